@@ -1,0 +1,67 @@
+"""TEST INFRASTRUCTURE ONLY. Import shim for the reference (pjh5672/llm-compressor at /root/reference).
+
+Only usable in the build container, where /root/reference is mounted. It is used by
+oracle/gen_golden.py to produce tests/golden/*.npz and by the (container-only) cross-checks of
+the oracle restatement.  Nothing in the product package, the -m gpu tests, smoke() or bench.py
+imports this file.
+
+The stubs replace import-time-only dependencies of the reference that are absent here
+(ref: llm_compressor/utils/general.py:10 matplotlib; utils/parser.py:4 easydict;
+quantization/calibrations/spinquant/hadamard_utils.py:3 fast_hadamard_transform).
+"""
+import importlib.machinery
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("LC_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "llm_compressor"))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+class EasyDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    __setattr__ = dict.__setitem__
+
+
+def install():
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+        except Exception:
+            _stub("matplotlib")
+            sys.modules["matplotlib"].pyplot = _stub("matplotlib.pyplot")
+    if "easydict" not in sys.modules:
+        try:
+            import easydict  # noqa: F401
+        except Exception:
+            _stub("easydict", EasyDict=EasyDict)
+    if "fast_hadamard_transform" not in sys.modules:
+        _stub("fast_hadamard_transform", hadamard_transform=None)
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+
+
+def build_quantizer(cfg):
+    install()
+    from llm_compressor.quantization.quant import FakeQuantizer
+
+    return FakeQuantizer.build(dict(cfg))
