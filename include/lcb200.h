@@ -1,0 +1,190 @@
+/*
+ * lcb200.h -- C ABI of the B200-native (sm_100a) compression hot path.
+ *
+ * Drop-in boundary for the data-parallel compression path of pjh5672/llm-compressor
+ * (reference tree: /root/reference/llm_compressor, cited below as ref:<file>:<lines>).
+ * The reference has no FFI of its own for this path -- it is pure PyTorch -- so each entry point
+ * replaces a group of tensor-op sequences inside one reference function.  The Python host side
+ * (llm_compressor_b200/*.py) mirrors the reference's quantizer / solver API on top of these
+ * calls through ctypes; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / CUDA types in the signatures.  `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`.
+ *   - no hidden allocation: scratch memory is passed in (`ws`, `ws_bytes`); each call has a
+ *     `*_ws_bytes` query.  Calls are asynchronous on `stream` and re-entrant.
+ *   - return value: LCB_OK or a negative LCB_ERR_*; lcb_last_error() gives a thread-local
+ *     message.  Numerical trouble found on the device (NaN scales, non-SPD Hessian) is reported
+ *     through the optional device word `status` (bit mask LCB_ST_*), which the caller reads
+ *     when it wants reference-equivalent exceptions (ref: int_quant.py:165, gptq/core.py:213-221).
+ *   - matrices are row-major and contiguous unless a leading dimension is given.
+ */
+#ifndef LCB200_H_
+#define LCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCB_ABI_VERSION 1
+
+#define LCB_OK 0
+#define LCB_ERR_INVALID (-1)     /* bad argument / geometry */
+#define LCB_ERR_UNSUPPORTED (-2) /* valid in the reference but not implemented here yet */
+#define LCB_ERR_CUDA (-3)        /* CUDA runtime / driver error, see lcb_last_error() */
+#define LCB_ERR_WORKSPACE (-4)   /* ws_bytes too small */
+
+/* device status bits */
+#define LCB_ST_NAN_SCALE 1u /* a scale is NaN  (ref: int_quant.py:165 assert) */
+#define LCB_ST_NOT_SPD 2u   /* Cholesky met a non-positive pivot (ref: gptq/core.py:213-221 retry) */
+
+/* storage / arithmetic dtype of a tensor: every primitive op rounds to this type, like torch */
+#define LCB_F32 0
+#define LCB_BF16 1
+
+/* quantizer families (ref: quantization/quant.py:36-63) */
+#define LCB_Q_INT 0  /* ref: quantizers/int_quant.py  */
+#define LCB_Q_FP 1   /* ref: quantizers/fp_quant.py   */
+#define LCB_Q_MX 2   /* ref: quantizers/mx_quant.py   */
+#define LCB_Q_NVFP 3 /* ref: quantizers/nvfp_quant.py */
+
+/* element formats, numbered like ElemFormat (ref: quantizers/formats.py:11-16) */
+#define LCB_E_INT4 1
+#define LCB_E_INT8 2
+#define LCB_E_FP4_E2M1 3
+#define LCB_E_FP8_E4M3 4
+#define LCB_E_FP8_E5M2 5
+
+typedef struct lcb_quant_cfg {
+  int32_t qtype;       /* LCB_Q_* */
+  int32_t elem;        /* LCB_E_* */
+  int32_t zero_point;  /* asymmetric */
+  int32_t scale_ebits; /* MX shared-exponent bits (ref: mx_quant.py:63), 8 */
+  int32_t reserved[4];
+} lcb_quant_cfg;
+
+/* mode bits of lcb_qdq */
+#define LCB_QDQ_FIND 1  /* compute scales / zeros from x (find_params) */
+#define LCB_QDQ_APPLY 2 /* write the fake-quantised tensor (fake_quantize) */
+
+int lcb_abi_version(void);
+const char* lcb_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench accounting) */
+uint64_t lcb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (c) fused quantize-dequantize.
+ * Replaces <Quantizer>.find_params / .forward / .fake_quantize together with
+ * _reshape_to_blocks / _undo_reshape_to_blocks / _quantize_elemwise_core
+ * (ref: int_quant.py:80-212, fp_quant.py:92-234, mx_quant.py:74-201, nvfp_quant.py:72-200,
+ *  utils.py:85-167,218-284).
+ *
+ * x, out : [batch, rows, cols] contiguous, dtype `dtype`.
+ * axis   : -1 groups of `group` consecutive elements along cols (ragged tail zero padded for
+ *             the statistics, like utils.py:119-132); -2 groups of `group` rows, per column.
+ * group  : > 0 group length; 0 = per tensor (INT / FP only; axis ignored).
+ *          Per-token is group = cols with axis -1, per-channel group = rows with axis -2.
+ * scales, zeros : block shaped, [batch*rows, G] (axis -1, G = ceil(cols/group)) or
+ *          [batch, G, cols] (axis -2, G = ceil(rows/group)); dtype `dtype`; per tensor: one
+ *          float32 each (torch keeps 0-dim parameters in fp32).  Outputs when mode has
+ *          LCB_QDQ_FIND (may be NULL), inputs otherwise.
+ * codes  : optional uint8 [batch, rows, cols]: the integer code (INT, two's complement int8) or
+ *          the element's bit pattern in its fp4 / fp8 format (low bits).
+ * NVFP needs the amax of the WHOLE tensor passed in (ref: nvfp_quant.py:87); with row-sharded
+ * multi-GPU use lcb_nvfp_global_amax + an all-reduce(MAX) and pass the result in nv_amax
+ * (device float, NULL = compute locally).
+ */
+size_t lcb_qdq_ws_bytes(const lcb_quant_cfg* cfg, int dtype, int64_t batch, int64_t rows, int64_t cols,
+                        int axis, int64_t group);
+int lcb_qdq(const lcb_quant_cfg* cfg, int dtype, int mode, const void* x, void* out, int64_t batch,
+            int64_t rows, int64_t cols, int axis, int64_t group, void* scales, void* zeros, uint8_t* codes,
+            const float* nv_amax, void* ws, size_t ws_bytes, uint32_t* status, void* stream);
+/* phase 1 of NVFP alone: amax_out[0] = max over blocks of |block maximum| (float32) */
+int lcb_nvfp_global_amax(const lcb_quant_cfg* cfg, int dtype, const void* x, int64_t batch, int64_t rows,
+                         int64_t cols, int axis, int64_t group, float* amax_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a) calibration statistics.
+ * lcb_hessian_accum replaces the body of cache_hessian_weight / Wrapper.cache_hessian_weight
+ * (ref: gptq/core.py:103-119, sparsegpt/core.py:85-101) and, with dxxt / x_fp given,
+ * cache_hessian_dxxt_weight (ref: gptaq/core.py:116-141):
+ *     H = beta*H + alpha * X^T X          dXXT = beta*dXXT + alpha * (X_fp - X)^T X
+ * X, X_fp: [tokens, k] bf16 row-major (token-major, as the hook receives them).
+ * H, dXXT: [k, k] float32.  The hook semantics are beta = n/(n+1), alpha = 2/(n+1); a
+ * token-sharded rank passes beta = 1, alpha = 1 and scales once after the all-reduce.
+ * Requires k % 8 == 0.  Tensor-core path: tcgen05 (bf16 x bf16 -> fp32 in TMEM).
+ */
+size_t lcb_hessian_ws_bytes(int64_t tokens, int64_t k);
+int lcb_hessian_accum(float* H, float* dxxt, const void* x, const void* x_fp, int64_t tokens, int64_t k,
+                      float alpha, float beta, void* ws, size_t ws_bytes, void* stream);
+/* ref: wanda/core.py:92-105, ria/core.py:94-107:  s = beta*s + alpha * sum_t X[t,:]^2 */
+int lcb_rownorm_accum(float* s, const void* x, int64_t tokens, int64_t k, float alpha, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) layer solvers.
+ * lcb_hessian_dead_fix: dead = diag(H) == 0; H[dead, dead] = 1 (ref: gptq/core.py:175-176); the
+ * caller zeroes W[:, dead] (and dXXT[:, dead]) itself.  dead: uint8 [k] out (may be NULL).
+ *
+ * lcb_chol_inv_upper replaces damping + cholesky -> cholesky_inverse -> cholesky(upper)
+ * (ref: gptq/core.py:207-224) and the act-order permutation of H (ref: gptq/core.py:181-201):
+ * with Hp[i][j] = H[perm[i]][perm[j]] (perm NULL = identity) and Hp += damp * mean(diag(H)) * I,
+ * U [k, k] (may alias H) receives the upper triangular factor with Hp^-1 = U^T U (strictly lower
+ * part zeroed).
+ * U is obtained as the inverse of the reverse-ordered Cholesky factor (H = R R^T, U = R^-1):
+ * one blocked potrf + one blocked trtri instead of the reference's potrf + potri + potrf.
+ * A non-positive pivot sets LCB_ST_NOT_SPD in *status (U is then garbage; the caller calls again
+ * with the larger damping, reproducing the reference's retry).
+ */
+int lcb_hessian_dead_fix(float* H, int64_t k, uint8_t* dead, void* stream);
+size_t lcb_chol_ws_bytes(int64_t k);
+int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int64_t* perm, float damp, void* ws,
+                       size_t ws_bytes, uint32_t* status, void* stream);
+
+/* Block loop of gptq.update_weight / gptaq.update_weight (ref: gptq/core.py:226-265,
+ * gptaq/core.py:274-319) on already permuted data:
+ *   W      [n, k] float32 in/out scratch (permuted weight, dead columns zeroed)
+ *   Q      [n, k] float32 out (dequantised result, still permuted)
+ *   U      [k, k] float32 upper factor from lcb_chol_inv_upper
+ *   P      [k, k] float32 or NULL (GPTAQ: alpha * triu(dXXT U^T, 1) U)
+ *   scales, zeros [n, G] float32 (G = k/group; per-row / per-tensor: G = 1), from lcb_qdq(FIND)
+ *   keep   [n, k] uint8 or NULL: 1 where the original weight was non-zero (MASK)
+ *   group  >0: grouped branch (group | block); -1 or 0: per-column branch
+ */
+size_t lcb_gptq_ws_bytes(int64_t n, int64_t k, int block);
+int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, const float* U, const float* P, const float* scales,
+                    const float* zeros, const uint8_t* keep, int64_t n, int64_t k, int64_t group, int block,
+                    void* ws, size_t ws_bytes, void* stream);
+/* P = alpha * triu(dXXT @ U^T, 1) @ U   (ref: gptaq/core.py:272); dXXT is overwritten */
+int lcb_gptaq_p(float* P, float* dxxt, const float* U, int64_t k, float alpha, void* ws, size_t ws_bytes, void* stream);
+
+/* Block loop of sparsegpt.prune_weight (ref: sparsegpt/core.py:192-218); W [n,k] fp32 in/out. */
+size_t lcb_sparsegpt_ws_bytes(int64_t n, int64_t k, int block);
+int lcb_sparsegpt_update(float* W, const float* U, double sparsity, int64_t n, int64_t k, int block, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (d) mask selection.  mask: uint8 [n, k], 1 = prune.
+ * lcb_mask_wanda : ref: wanda/core.py:116-126 (per row, k_prune = int(k*ratio) smallest by
+ *                  (|W|*sqrt(s), column index)).
+ * lcb_mask_magnitude : ref: magnitude/core.py:38-43 (global threshold, <=).
+ * lcb_mask_ria   : ref: ria/core.py:118-126.
+ * W: [n, k] dtype `dtype`.  scaler_row: [k] float32.
+ */
+size_t lcb_mask_ws_bytes(int64_t n, int64_t k);
+int lcb_mask_wanda(const void* W, int dtype, const float* scaler_row, uint8_t* mask, int64_t n, int64_t k,
+                   double ratio, void* ws, size_t ws_bytes, void* stream);
+int lcb_mask_magnitude(const void* W, int dtype, uint8_t* mask, int64_t n, int64_t k, double ratio, void* ws,
+                       size_t ws_bytes, void* stream);
+int lcb_mask_ria(const void* W, int dtype, const float* scaler_row, uint8_t* mask, int64_t n, int64_t k, double ratio,
+                 float alpha, void* ws, size_t ws_bytes, void* stream);
+/* W[mask] = 0 in place */
+int lcb_apply_mask(void* W, int dtype, const uint8_t* mask, int64_t numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCB200_H_ */

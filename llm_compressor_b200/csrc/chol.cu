@@ -1,0 +1,240 @@
+// (b) Cholesky-inverse stage of the layer solvers.
+//
+// The reference computes  U = cholesky( cholesky_inverse( cholesky(H) ), upper )
+// (ref: gptq/core.py:213-224, gptaq/core.py:258-269, sparsegpt/core.py:179-190), i.e. the upper
+// factor of H^-1 = U^T U.  Algebraically U = R^-1 where H = R R^T with R upper triangular, and R is
+// the index-reversed lower Cholesky factor of the index-reversed matrix.  So instead of
+// potrf + potri + potrf (4K^3/3 flop) this file does ONE hand-written blocked Cholesky of J H J
+// and ONE blocked triangular inverse (2K^3/3 flop), writing J L^-1 J back as U:
+//   1. gather (optional act-order permutation) + index reversal + damping  -> work matrix
+//   2. right-looking blocked potrf, 128-wide panels: diagonal block factored (and inverted) by
+//      one CTA in shared memory, panel TRSM and trailing SYRK as fp32 GEMMs
+//   3. recursive blocked triangular inverse: batched GEMMs per level (log2(K/128) levels)
+#include "linalg.cuh"
+
+namespace lcb {
+
+namespace {
+
+constexpr int NB = 128;
+constexpr int LDT = NB + 1;  // padded shared-memory row stride (bank-conflict free column access)
+
+// H[dead,dead] = 1 where diag(H) == 0 (ref: gptq/core.py:175-176); dead flags out.
+__global__ void dead_fix_kernel(float* H, int64_t k, uint8_t* dead) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const bool d = H[i * k + i] == 0.0f;
+  if (d) H[i * k + i] = 1.0f;
+  if (dead) dead[i] = d ? 1 : 0;
+}
+
+// out[0] = sum(diag(H)) (single CTA; k <= 16K so this is tiny)
+__global__ void diag_sum_kernel(const float* H, int64_t k, float* out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < k; i += blockDim.x) s += H[i * k + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = s;
+  }
+}
+
+// A[i][j] = H[p(k-1-i)][p(k-1-j)] + (i == j) * damp * mean(diag H)     (perm optional)
+__global__ void gather_reverse_damp_kernel(float* __restrict__ A, const float* __restrict__ H,
+                                           const int64_t* __restrict__ perm, int64_t k, float damp,
+                                           const float* diag_sum) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= k) return;
+  int64_t si = k - 1 - i, sj = k - 1 - j;
+  if (perm) { si = perm[si]; sj = perm[sj]; }
+  float v = H[si * k + sj];
+  if (i == j) v += damp * (diag_sum[0] / (float)k);
+  A[i * k + j] = v;
+}
+
+// U[i][j] = Linv[k-1-i][k-1-j]  (Linv lower triangular with zero upper part -> U upper)
+__global__ void reverse_out_kernel(float* __restrict__ U, const float* __restrict__ Linv, int64_t k) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= k) return;
+  U[i * k + j] = (j >= i) ? Linv[(k - 1 - i) * k + (k - 1 - j)] : 0.0f;
+}
+
+__global__ void zero_strict_upper_kernel(float* A, int64_t k) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j < k && j > i) A[i * k + j] = 0.0f;
+}
+
+// One CTA (128 threads): Cholesky of the nb x nb diagonal block at A (ld) in shared memory, left
+// looking, thread i owns row i.  Also the inverse of the factor (column j per thread, forward
+// substitution) to `dinv` [nb x NB], used to turn the panel TRSM into a GEMM.
+__global__ void __launch_bounds__(NB) potf2_inv_kernel(float* A, int64_t ld, int nb, float* dinv, uint32_t* status) {
+  extern __shared__ float sm[];
+  float* L = sm;             // [NB][LDT]
+  float* X = sm + NB * LDT;  // [NB][LDT]
+  const int i = threadIdx.x;
+  for (int r = 0; r < nb; ++r) L[r * LDT + i] = (i < nb && i <= r) ? A[(int64_t)r * ld + i] : 0.0f;
+  __syncthreads();
+  bool bad = false;
+  for (int j = 0; j < nb; ++j) {
+    __syncthreads();  // column j-1 (written by other threads) is visible
+    float v = 0.f;
+    if (i >= j && i < nb) {
+      v = L[i * LDT + j];
+      for (int k = 0; k < j; ++k) v = fmaf(-L[i * LDT + k], L[j * LDT + k], v);
+    }
+    if (i == j) {
+      if (!(v > 0.0f)) bad = true;
+      L[j * LDT + j] = sqrtf(v);
+    }
+    __syncthreads();
+    if (i > j && i < nb) L[i * LDT + j] = v / L[j * LDT + j];
+  }
+  __syncthreads();
+  if (bad && status) atomicOr(status, LCB_ST_NOT_SPD);
+  // inverse: thread j computes column j of X = L^-1
+  const int j = i;
+  if (j < nb) {
+    for (int r = 0; r < j; ++r) X[r * LDT + j] = 0.0f;
+    X[j * LDT + j] = 1.0f / L[j * LDT + j];
+    for (int r = j + 1; r < nb; ++r) {
+      float s = 0.f;
+      for (int k = j; k < r; ++k) s = fmaf(L[r * LDT + k], X[k * LDT + j], s);
+      X[r * LDT + j] = -s / L[r * LDT + r];
+    }
+  }
+  __syncthreads();
+  for (int r = 0; r < nb; ++r) {
+    if (i < nb) {
+      A[(int64_t)r * ld + i] = (i <= r) ? L[r * LDT + i] : 0.0f;
+      dinv[r * NB + i] = X[r * LDT + i];
+    }
+  }
+}
+
+// copy the inverted diagonal blocks (dinv_all: [nblk][NB][NB]) onto the diagonal of A
+__global__ void put_diag_blocks_kernel(float* A, int64_t k, const float* dinv_all) {
+  const int b = blockIdx.x;
+  const int nb = (int)min((int64_t)NB, k - (int64_t)b * NB);
+  for (int e = threadIdx.x; e < nb * NB; e += blockDim.x) {
+    const int r = e / NB, c = e % NB;
+    if (c < nb) A[((int64_t)b * NB + r) * k + (int64_t)b * NB + c] = dinv_all[(int64_t)b * NB * NB + r * NB + c];
+  }
+}
+
+}  // namespace
+
+static size_t chol_ws_floats(int64_t k) {
+  const int64_t nblk = ceil_div(k, NB);
+  return (size_t)(k * k)            // work matrix
+         + (size_t)(k * k / 2 + k * NB)  // T of the trtri recursion
+         + (size_t)(nblk * NB * NB)  // inverted diagonal blocks
+         + (size_t)(k * NB)          // TRSM panel
+         + 64;
+}
+
+}  // namespace lcb
+
+using namespace lcb;
+
+extern "C" size_t lcb_chol_ws_bytes(int64_t k) { return chol_ws_floats(k) * sizeof(float); }
+
+extern "C" int lcb_hessian_dead_fix(float* H, int64_t k, uint8_t* dead, void* stream) {
+  LCB_REQUIRE(H != nullptr && k > 0, "lcb_hessian_dead_fix: bad arguments");
+  dead_fix_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(H, k, dead);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int64_t* perm, float damp, void* ws,
+                                  size_t ws_bytes, uint32_t* status, void* stream) {
+  LCB_REQUIRE(H != nullptr && U != nullptr && k > 0, "lcb_chol_inv_upper: bad arguments");
+  if (ws == nullptr || ws_bytes < lcb_chol_ws_bytes(k)) {
+    set_error("lcb_chol_inv_upper: workspace of %zu bytes needed, %zu given", lcb_chol_ws_bytes(k), ws_bytes);
+    return LCB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t nblk = ceil_div(k, NB);
+  float* A = static_cast<float*>(ws);
+  float* T = A + k * k;
+  float* dinv_all = T + (k * k / 2 + k * NB);
+  float* panel = dinv_all + nblk * NB * NB;
+  float* dsum = panel + k * NB;
+
+  static bool attr_set = false;
+  const int smem = 2 * NB * LDT * (int)sizeof(float);
+  if (!attr_set) {
+    LCB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+
+  diag_sum_kernel<<<1, 1024, 0, st>>>(H, k, dsum);
+  LCB_LAUNCH_CHECK();
+  dim3 g2((unsigned)ceil_div(k, 256), (unsigned)k);
+  gather_reverse_damp_kernel<<<g2, 256, 0, st>>>(A, H, perm, k, damp, dsum);
+  LCB_LAUNCH_CHECK();
+
+  // ---- blocked right-looking Cholesky (lower) of A
+  for (int64_t b = 0; b < nblk; ++b) {
+    const int64_t j = b * NB;
+    const int nb = (int)std::min<int64_t>(NB, k - j);
+    float* Ajj = A + j * k + j;
+    float* dinv = dinv_all + b * NB * NB;
+    potf2_inv_kernel<<<1, NB, smem, st>>>(Ajj, k, nb, dinv, status);
+    LCB_LAUNCH_CHECK();
+    const int64_t m2 = k - j - nb;
+    if (m2 <= 0) break;
+    float* A21 = A + (j + nb) * k + j;
+    // L21 = A21 * L11^-T   (panel, ld NB)
+    int rc = sgemm(gemm_args(A21, k, dinv, NB, panel, NB, (int)m2, nb, nb, 1.0f, 0.0f, /*transB=*/1), st);
+    if (rc != LCB_OK) return rc;
+    LCB_CUDA(cudaMemcpy2DAsync(A21, (size_t)k * sizeof(float), panel, NB * sizeof(float), (size_t)nb * sizeof(float),
+                               (size_t)m2, cudaMemcpyDeviceToDevice, st));
+    // A22 -= L21 * L21^T   (lower tiles only)
+    rc = sgemm(gemm_args(panel, NB, panel, NB, A + (j + nb) * k + (j + nb), k, (int)m2, (int)m2, nb, -1.0f, 1.0f, 1,
+                         GEMM_LOWER_OUT), st);
+    if (rc != LCB_OK) return rc;
+  }
+  zero_strict_upper_kernel<<<g2, 256, 0, st>>>(A, k);
+  LCB_LAUNCH_CHECK();
+  put_diag_blocks_kernel<<<(unsigned)nblk, 256, 0, st>>>(A, k, dinv_all);
+  LCB_LAUNCH_CHECK();
+
+  // ---- recursive triangular inverse, in place: [[A,0],[C,B]]^-1 = [[A^-1,0],[-B^-1 C A^-1, B^-1]]
+  for (int64_t s = NB; s < k; s *= 2) {
+    const int64_t nodes = ceil_div(k, 2 * s);
+    for (int64_t t0 = 0; t0 < nodes;) {
+      // batch consecutive nodes with the same (full) size; the ragged last node goes alone
+      const int64_t base = t0 * 2 * s;
+      const int64_t sB0 = std::min<int64_t>(s, k - base - s);
+      if (sB0 <= 0) break;
+      int64_t cnt = 1;
+      if (sB0 == s) {
+        while (t0 + cnt < nodes && (k - (t0 + cnt) * 2 * s - s) >= s) ++cnt;
+      }
+      float* Ainv = A + base * k + base;
+      float* Cblk = A + (base + s) * k + base;
+      float* Binv = A + (base + s) * k + (base + s);
+      GemmArgs g1 = gemm_args(Cblk, k, Ainv, k, T, s, (int)sB0, (int)s, (int)s, 1.0f, 0.0f, 0, GEMM_B_LOWER);
+      g1.batch = (int)cnt; g1.strideA = g1.strideB = 2 * s * (k + 1); g1.strideC = s * s;
+      int rc = sgemm(g1, st);
+      if (rc != LCB_OK) return rc;
+      GemmArgs g2a = gemm_args(Binv, k, T, s, Cblk, k, (int)sB0, (int)s, (int)sB0, -1.0f, 0.0f, 0, GEMM_A_LOWER);
+      g2a.batch = (int)cnt; g2a.strideA = g2a.strideC = 2 * s * (k + 1); g2a.strideB = s * s;
+      rc = sgemm(g2a, st);
+      if (rc != LCB_OK) return rc;
+      t0 += cnt;
+    }
+  }
+  reverse_out_kernel<<<g2, 256, 0, st>>>(U, A, k);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}

@@ -1,0 +1,409 @@
+// (a) Calibration statistics on the 5th-generation tensor cores.
+//
+//   H    = beta * H    + alpha * X^T X             ref: gptq/core.py:103-119, sparsegpt/core.py:85-101
+//   dXXT = beta * dXXT + alpha * (X_fp - X)^T X    ref: gptaq/core.py:116-141
+//   s    = beta * s    + alpha * sum_t X[t,:]^2    ref: wanda/core.py:92-105
+//
+// X is the token-major bf16 activation [T, K] exactly as the forward hook receives it, so both MMA
+// operands are "MN-major" views of the same tensor: A = X[:, m-tile]^T, B = X[:, n-tile]^T with
+// the token axis as the reduction dimension.  TMA (128B swizzle, 64-channel x 64-token boxes)
+// stages the operands in shared memory, one elected thread issues tcgen05.mma (M=128, N=256,
+// K=16, bf16 x bf16 -> fp32) into TMEM, and four epilogue warps read the accumulator back with
+// tcgen05.ld and apply the running-mean update to H in place.  bf16 products are exact in fp32,
+// so the result differs from the reference's fp32 SGEMM only by summation order.
+//
+// Persistent kernel: one CTA per SM walks the output tiles; two 256-column TMEM accumulators let
+// the epilogue of tile i overlap the MMAs of tile i+1; a 4-stage smem ring decouples TMA from MMA.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace lcb {
+
+namespace {
+
+constexpr int BM = 128;         // UMMA M (rows of the H tile)
+constexpr int BN = 256;         // UMMA N (columns of the H tile)
+constexpr int BKT = 64;         // tokens per pipeline stage
+constexpr int UMMA_K = 16;      // tokens per tcgen05.mma (bf16)
+constexpr int STAGES = 4;
+constexpr int BOX_C = 64;       // channels per TMA box (64 * 2 B = one 128 B swizzle row)
+constexpr int BOX_BYTES = BOX_C * BKT * 2;          // 8192
+constexpr int A_STAGE_BYTES = (BM / BOX_C) * BOX_BYTES;  // 16384
+constexpr int B_STAGE_BYTES = (BN / BOX_C) * BOX_BYTES;  // 32768
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int NUM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int TMEM_COLS = 512;    // two accumulators of BN fp32 columns
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, MN-major operand, 128B swizzle (cute::UMMA::SmemDescriptor):
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (stride between 64-channel
+//   chunks), [32,46) stride byte offset >> 4 (stride between 8-token groups), [46,48) version = 1,
+//   [61,64) layout type (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((BOX_BYTES >> 4) & 0x3fff) << 16;  // LBO: next 64-channel box
+  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;       // SBO: next 8 tokens (8 rows of 128 B)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format BF16 (1)
+// at [7,10)/[10,13), a_major / b_major = MN (1) at 15 / 16, N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+struct HessArgs {
+  float* H;
+  int64_t k;       // channels
+  int64_t tokens;
+  float alpha, beta;
+  int tiles_m, tiles_n;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, HessArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                  // [STAGES]   TMA -> MMA
+  uint64_t* empty = bars + STAGES;        // [STAGES]   MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;    // [2]        MMA -> epilogue
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = a.tiles_m * a.tiles_n;
+  const int kblocks = (int)((a.tokens + BKT - 1) / BKT);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int h = 0; h < BM / BOX_C; ++h) tma_load_2d(&map_a, &full[stage], sa + h * BOX_BYTES, m0 + h * BOX_C, kb * BKT);
+#pragma unroll
+          for (int h = 0; h < BN / BOX_C; ++h) tma_load_2d(&map_b, &full[stage], sb + h * BOX_BYTES, n0 + h * BOX_C, kb * BKT);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc();
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BKT / UMMA_K; ++k) {
+            // 16 tokens = 16 swizzled rows of 128 B = 2048 B further into each 64-channel box
+            const uint64_t da = make_desc(sa + k * UMMA_K * 128);
+            const uint64_t db = make_desc(sb + k * UMMA_K * 128);
+            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> H (in place) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
+      mbar_wait(&tfull[as], aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+        const int64_t col0 = (int64_t)n0 + c * 32;
+        if (row < a.k && col0 < a.k) {
+          float* hp = a.H + row * a.k + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < a.k) {  // k % 8 == 0: a float4 is entirely in or out
+              float4 o;
+              if (a.beta != 0.0f) {
+                const float4 old = *reinterpret_cast<const float4*>(hp + j);
+                o.x = fmaf(a.alpha, v[j + 0], a.beta * old.x); o.y = fmaf(a.alpha, v[j + 1], a.beta * old.y);
+                o.z = fmaf(a.alpha, v[j + 2], a.beta * old.z); o.w = fmaf(a.alpha, v[j + 3], a.beta * old.w);
+              } else {
+                o.x = a.alpha * v[j + 0]; o.y = a.alpha * v[j + 1]; o.z = a.alpha * v[j + 2]; o.w = a.alpha * v[j + 3];
+              }
+              *reinterpret_cast<float4*>(hp + j) = o;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
+// dX split for GPTAQ: d = X_fp - X (exact in fp32 for bf16 inputs of similar magnitude),
+// hi = bf16(d), lo = bf16(d - hi)  ->  d^T X = hi^T X + lo^T X with ~16 mantissa bits of d.
+__global__ void dx_split_kernel(const __nv_bfloat16* __restrict__ xfp, const __nv_bfloat16* __restrict__ x,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = __fsub_rn(__bfloat162float(xfp[i]), __bfloat162float(x[i]));
+    const __nv_bfloat16 h = __float2bfloat16_rn(d);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(__fsub_rn(d, __bfloat162float(h)));
+  }
+}
+
+// s[k] = beta * s[k] + alpha * sum_t x[t][k]^2      (32 x 8 threads: 64 channels per CTA)
+__global__ void __launch_bounds__(256) rownorm_kernel(float* __restrict__ s, const __nv_bfloat16* __restrict__ x,
+                                                      int64_t tokens, int64_t k, float alpha, float beta) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 64 + tx * 2;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < k) {  // k is even
+    for (int64_t t = ty; t < tokens; t += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + t * k + c);
+      const float f0 = __bfloat162float(v.x), f1 = __bfloat162float(v.y);
+      a0 = fmaf(f0, f0, a0); a1 = fmaf(f1, f1, a1);
+    }
+  }
+  red[ty][tx * 2] = a0; red[ty][tx * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int64_t cc = (int64_t)blockIdx.x * 64 + threadIdx.x;
+    if (cc < k) {
+      float acc = 0.f;
+      for (int i = 0; i < 8; ++i) acc += red[i][threadIdx.x];
+      s[cc] = (beta != 0.0f ? beta * s[cc] : 0.0f) + alpha * acc;
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver (cudaGetDriverEntryPoint: %d / %d)", (int)e, (int)q);
+      return LCB_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return LCB_OK;
+}
+
+// [tokens, k] bf16 row-major -> 2D map, dim0 = channels (contiguous), dim1 = tokens, 64 x 64 boxes
+int make_x_map(CUtensorMap* map, const void* x, int64_t tokens, int64_t k) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc != LCB_OK) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)tokens};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  cuuint32_t box[2] = {BOX_C, BKT};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (x=%p tokens=%lld k=%lld)", (int)r, x, (long long)tokens,
+              (long long)k);
+    return LCB_ERR_CUDA;
+  }
+  return LCB_OK;
+}
+
+int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens, int64_t k, float alpha, float beta,
+               cudaStream_t st) {
+  CUtensorMap map_a, map_b;
+  int rc = make_x_map(&map_a, a_src, tokens, k);
+  if (rc != LCB_OK) return rc;
+  rc = make_x_map(&map_b, b_src, tokens, k);
+  if (rc != LCB_OK) return rc;
+  HessArgs a{};
+  a.H = out; a.k = k; a.tokens = tokens; a.alpha = alpha; a.beta = beta;
+  a.tiles_m = (int)ceil_div(k, BM); a.tiles_n = (int)ceil_div(k, BN);
+  static bool attr = false;
+  if (!attr) {
+    LCB_CUDA(cudaFuncSetAttribute(hessian_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  const int tiles = a.tiles_m * a.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  hessian_umma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, a);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+}  // namespace
+
+}  // namespace lcb
+
+using namespace lcb;
+
+extern "C" size_t lcb_hessian_ws_bytes(int64_t tokens, int64_t k) { return (size_t)(tokens * k) * 2 * 2 + 256; }
+
+extern "C" int lcb_hessian_accum(float* H, float* dxxt, const void* x, const void* x_fp, int64_t tokens, int64_t k,
+                                 float alpha, float beta, void* ws, size_t ws_bytes, void* stream) {
+  LCB_REQUIRE(H != nullptr && x != nullptr, "lcb_hessian_accum: NULL pointer");
+  LCB_REQUIRE(tokens > 0 && k > 0 && k % 8 == 0, "lcb_hessian_accum: need tokens > 0 and k a positive multiple of 8");
+  LCB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0,
+              "lcb_hessian_accum: x and H must be 16-byte aligned");
+  LCB_REQUIRE((dxxt == nullptr) == (x_fp == nullptr), "lcb_hessian_accum: dxxt and x_fp go together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = launch_xtx(H, x, x, tokens, k, alpha, beta, st);
+  if (rc != LCB_OK) return rc;
+  if (dxxt != nullptr) {
+    if (ws == nullptr || ws_bytes < lcb_hessian_ws_bytes(tokens, k)) {
+      set_error("lcb_hessian_accum: workspace of %zu bytes needed for the dXXT term", lcb_hessian_ws_bytes(tokens, k));
+      return LCB_ERR_WORKSPACE;
+    }
+    LCB_REQUIRE((reinterpret_cast<uintptr_t>(x_fp) & 15) == 0 && (reinterpret_cast<uintptr_t>(dxxt) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(ws) & 255) == 0,
+                "lcb_hessian_accum: x_fp, dxxt (16 B) and ws (256 B) must be aligned");
+    __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* lo = hi + ((tokens * k + 127) / 128) * 128;
+    const int64_t n = tokens * k;
+    int64_t g = ceil_div(n, 256 * 4);
+    if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
+    dx_split_kernel<<<(unsigned)g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_fp),
+                                                  static_cast<const __nv_bfloat16*>(x), hi, lo, n);
+    LCB_LAUNCH_CHECK();
+    rc = launch_xtx(dxxt, hi, x, tokens, k, alpha, beta, st);
+    if (rc != LCB_OK) return rc;
+    rc = launch_xtx(dxxt, lo, x, tokens, k, alpha, 1.0f, st);
+    if (rc != LCB_OK) return rc;
+  }
+  return LCB_OK;
+}
+
+extern "C" int lcb_rownorm_accum(float* s, const void* x, int64_t tokens, int64_t k, float alpha, float beta,
+                                 void* stream) {
+  LCB_REQUIRE(s != nullptr && x != nullptr && tokens > 0 && k > 0 && k % 2 == 0, "lcb_rownorm_accum: bad arguments");
+  rownorm_kernel<<<(unsigned)ceil_div(k, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      s, static_cast<const __nv_bfloat16*>(x), tokens, k, alpha, beta);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}

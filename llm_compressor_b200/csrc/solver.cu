@@ -1,0 +1,308 @@
+// (b) Column-block quantize-and-error-propagate loops of GPTQ / GPTAQ / SparseGPT.
+//
+// ref: gptq/core.py:226-265, gptaq/core.py:274-319, sparsegpt/core.py:192-218.
+// One kernel launch per 128-column block does everything the reference does in its inner Python
+// loop (128 iterations x ~25 tiny kernels): quantise / mask the column (or the group), form the
+// error, and propagate it to the later columns of the block.  Rows are independent given U, so
+// a CTA owns 32 rows and never synchronises with other CTAs; 8 threads share a row (16 columns
+// each, held in registers), the 128x128 diagonal block of U (and P for GPTAQ) sits in shared
+// memory.  The trailing lazy-batch update W[:, i2:] -= Err @ U[i1:i2, i2:] is an fp32 GEMM.
+#include "linalg.cuh"
+#include "qmath.cuh"
+
+namespace lcb {
+
+namespace {
+
+constexpr int BLK = 128;           // column block (the reference's block_size)
+constexpr int CPT = 16;            // columns per thread
+constexpr int TPR = BLK / CPT;     // threads per row = 8
+constexpr int ROWS_PER_CTA = 32;   // 256 threads
+constexpr int ULD = BLK + 4;
+
+enum { MODE_QUANT = 0, MODE_SPARSE = 1 };
+
+struct BlockArgs {
+  float* W;           // [n, k] working weight (block columns are read; SPARSE: written back)
+  float* Q;           // [n, k] output (QUANT)
+  const float* U;     // [k, k]
+  const float* P;     // [k, k] or null
+  const float* scales;  // [n, G]
+  const float* zeros;
+  const uint8_t* keep;   // [n, k] or null
+  const uint8_t* prune;  // [n, BLK] (SPARSE) mask for this block
+  float* Err;         // [n, BLK]
+  float* W1out;       // [n, BLK] (GPTAQ) block after in-block updates, or null
+  int64_t n, k;
+  int64_t i1;         // first column of the block
+  int count;          // columns in the block (<= BLK)
+  int64_t group;      // > 0 grouped, <= 0 per column
+  int64_t G;          // parameter columns per row
+  QCfg c;
+};
+
+template <int MODE, bool HAS_P>
+__global__ void __launch_bounds__(256) block_step_kernel(BlockArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* Us = smem;                               // [BLK][ULD]
+  float* Ps = HAS_P ? smem + BLK * ULD : nullptr;  // [BLK][ULD]
+  const int t = threadIdx.x;
+  // stage the diagonal blocks (zero filled beyond `count`)
+  for (int e = t; e < BLK * BLK; e += 256) {
+    const int r = e / BLK, c = e % BLK;
+    const bool in = r < a.count && c < a.count;
+    Us[r * ULD + c] = in ? a.U[(a.i1 + r) * a.k + a.i1 + c] : 0.0f;
+    if (HAS_P) Ps[r * ULD + c] = in ? a.P[(a.i1 + r) * a.k + a.i1 + c] : 0.0f;
+  }
+  __syncthreads();
+
+  const int t8 = t % TPR;
+  const int64_t row = (int64_t)blockIdx.x * ROWS_PER_CTA + t / TPR;
+  const bool row_ok = row < a.n;
+  const int64_t rr = row_ok ? row : 0;
+  const int c0 = t8 * CPT;
+
+  float w[CPT], snap[CPT], qv[CPT], ev[CPT];
+  const float* wp = a.W + rr * a.k + a.i1 + c0;
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    w[j] = (row_ok && c0 + j < a.count) ? wp[j] : 0.0f;
+    snap[j] = w[j]; qv[j] = 0.0f; ev[j] = 0.0f;
+  }
+  uint32_t keepbits = 0xffffu, prunebits = 0u;
+  if (MODE == MODE_QUANT && a.keep && row_ok) {
+    keepbits = 0;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+      if (c0 + j < a.count && a.keep[rr * a.k + a.i1 + c0 + j]) keepbits |= 1u << j;
+  }
+  if (MODE == MODE_SPARSE && row_ok) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+      if (c0 + j < a.count && a.prune[rr * BLK + c0 + j]) prunebits |= 1u << j;
+  }
+  const bool grouped = (MODE == MODE_QUANT) && a.group > 0;
+  const int gs = grouped ? (int)a.group : 1;
+  float s_cur = 1.0f, z_cur = 0.0f;
+  if (MODE == MODE_QUANT && !grouped) {  // per-row parameters
+    s_cur = a.scales[rr * a.G];
+    z_cur = a.zeros[rr * a.G];
+  }
+  const bool need_prop = HAS_P || !grouped || gs < a.count;
+  const int lane = t & 31;
+  const int lane_row_base = lane - t8;  // lane of t8 == 0 for this row
+
+#pragma unroll 1
+  for (int ib = 0; ib < TPR; ++ib) {
+    if (ib * CPT >= a.count) break;
+    if (grouped && ((ib * CPT) % gs) == 0) {
+      // group entry: columns are quantised from their value at this point (ref :253-262)
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) snap[j] = w[j];
+      const int64_t g = (a.i1 + ib * CPT) / gs;
+      s_cur = a.scales[rr * a.G + g];
+      z_cur = a.zeros[rr * a.G + g];
+    }
+#pragma unroll
+    for (int ii = 0; ii < CPT; ++ii) {
+      const int i = ib * CPT + ii;
+      // value of column i as the quantiser sees it, broadcast from its owner thread
+      const float mine = grouped ? snap[ii] : w[ii];
+      const float wi = __shfl_sync(0xffffffffu, mine, lane_row_base + ib);
+      const uint32_t kb = __shfl_sync(0xffffffffu, MODE == MODE_QUANT ? keepbits : prunebits, lane_row_base + ib);
+      float q;
+      if (MODE == MODE_QUANT) {
+        float code;
+        q = fake_quant<LCB_F32>(a.c, wi, s_cur, z_cur, code);
+        q = ((kb >> ii) & 1u) ? q : 0.0f;  // q *= MASK (ref :244,258)
+      } else {
+        q = ((kb >> ii) & 1u) ? 0.0f : wi;  // q[MASK1[:, i]] = 0 (ref sparsegpt :209-210)
+      }
+      const float d = Us[i * ULD + i];
+      const float e = __fdiv_rn(__fsub_rn(wi, q), d);
+      if (t8 == ib) { qv[ii] = q; ev[ii] = e; }
+      // propagate to columns j >= i of the block: w_j -= e * U[i][j] (- w_i * P[i][j]).
+      // With one group spanning the whole block and no P nothing downstream reads the result.
+      if (need_prop && i < a.count && t8 >= ib) {
+        const float* urow = Us + i * ULD + c0;
+        const float* prow = HAS_P ? Ps + i * ULD + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          if (t8 > ib || j >= ii) {
+            float upd = __fmul_rn(e, urow[j]);
+            if (HAS_P) upd = __fsub_rn(upd, __fmul_rn(wi, prow[j]));
+            w[j] = __fsub_rn(w[j], upd);
+          }
+        }
+      }
+    }
+  }
+
+  if (!row_ok) return;
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    if (c0 + j < a.count) {
+      if (MODE == MODE_QUANT) a.Q[rr * a.k + a.i1 + c0 + j] = qv[j];
+      else a.W[rr * a.k + a.i1 + c0 + j] = qv[j];
+    }
+    a.Err[rr * BLK + c0 + j] = (c0 + j < a.count) ? ev[j] : 0.0f;
+    if (a.W1out) a.W1out[rr * BLK + c0 + j] = (c0 + j < a.count) ? w[j] : 0.0f;
+  }
+}
+
+// SparseGPT saliency of one block: tmp = W1^2 / diag(U1)^2  (ref: sparsegpt/core.py:201)
+__global__ void sparse_metric_kernel(const float* W, const float* U, float* metric, int64_t n, int64_t k, int64_t i1,
+                                     int count) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * count) return;
+  const int64_t r = idx / count;
+  const int c = (int)(idx % count);
+  const float w = W[r * k + i1 + c];
+  const float d = U[(i1 + c) * k + i1 + c];
+  metric[idx] = __fdiv_rn(__fmul_rn(w, w), __fmul_rn(d, d));
+}
+
+__global__ void sparse_mask_kernel(const float* metric, const float* thresh, uint8_t* prune, int64_t n, int count) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * count) return;
+  const int64_t r = idx / count;
+  const int c = (int)(idx % count);
+  prune[r * BLK + c] = metric[idx] <= thresh[0];
+}
+
+}  // namespace
+
+// exact k-th smallest (0-based index `kth`) of n non-negative-or-any fp32 values (masks.cu)
+int select_kth_f32(const float* vals, int64_t n, int64_t kth, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t select_ws_bytes();
+
+}  // namespace lcb
+
+using namespace lcb;
+
+static size_t gptq_ws_floats(int64_t n, int block) { return (size_t)(2 * n * block + 64); }
+
+extern "C" size_t lcb_gptq_ws_bytes(int64_t n, int64_t k, int block) {
+  (void)k;
+  return gptq_ws_floats(n, block) * sizeof(float);
+}
+
+extern "C" int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, const float* U, const float* P,
+                               const float* scales, const float* zeros, const uint8_t* keep, int64_t n, int64_t k,
+                               int64_t group, int block, void* ws, size_t ws_bytes, void* stream) {
+  LCB_REQUIRE(cfg && W && Q && U && scales && zeros, "lcb_gptq_update: NULL pointer");
+  LCB_REQUIRE(block == BLK, "lcb_gptq_update: block must be 128 (the reference's block_size)");
+  LCB_REQUIRE(n > 0 && k > 0, "lcb_gptq_update: bad shape");
+  if (group > 0) {
+    LCB_REQUIRE(BLK % group == 0 && group % CPT == 0 && k % group == 0,
+                "lcb_gptq_update: group must divide 128, be a multiple of 16 and divide k (got %lld)", (long long)group);
+  }
+  if (ws == nullptr || ws_bytes < lcb_gptq_ws_bytes(n, k, block)) {
+    set_error("lcb_gptq_update: workspace of %zu bytes needed", lcb_gptq_ws_bytes(n, k, block));
+    return LCB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BlockArgs a{};
+  a.W = W; a.Q = Q; a.U = U; a.P = P; a.scales = scales; a.zeros = zeros; a.keep = keep;
+  a.Err = static_cast<float*>(ws);
+  a.W1out = P ? a.Err + n * BLK : nullptr;
+  a.n = n; a.k = k; a.group = group; a.G = group > 0 ? k / group : 1;
+  a.c.qtype = cfg->qtype; a.c.zero_point = cfg->zero_point ? 1 : 0;
+  a.c.scale_emax = (float)((1 << ((cfg->scale_ebits > 0 ? cfg->scale_ebits : 8) - 1)) - 1);
+  a.c.f = make_fmt(cfg->elem);
+  const int smem = (P ? 2 : 1) * BLK * ULD * (int)sizeof(float);
+  LCB_CUDA(cudaFuncSetAttribute(block_step_kernel<MODE_QUANT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  LCB_CUDA(cudaFuncSetAttribute(block_step_kernel<MODE_QUANT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const unsigned grid = (unsigned)ceil_div(n, ROWS_PER_CTA);
+  for (int64_t i1 = 0; i1 < k; i1 += BLK) {
+    const int64_t i2 = std::min<int64_t>(i1 + BLK, k);
+    a.i1 = i1; a.count = (int)(i2 - i1);
+    if (P) block_step_kernel<MODE_QUANT, true><<<grid, 256, smem, st>>>(a);
+    else block_step_kernel<MODE_QUANT, false><<<grid, 256, smem, st>>>(a);
+    LCB_LAUNCH_CHECK();
+    if (i2 < k) {
+      // W[:, i2:] -= Err1 @ U[i1:i2, i2:]  (- W1 @ P[i1:i2, i2:])      ref gptq :265, gptaq :319
+      int rc = sgemm(gemm_args(a.Err, BLK, U + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), a.count, -1.0f, 1.0f, 0), st);
+      if (rc != LCB_OK) return rc;
+      if (P) {
+        rc = sgemm(gemm_args(a.W1out, BLK, P + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), a.count, 1.0f, 1.0f, 0), st);
+        if (rc != LCB_OK) return rc;
+      }
+    }
+  }
+  return LCB_OK;
+}
+
+// P = alpha * triu(dXXT @ U^T, 1) @ U   (ref: gptaq/core.py:272)
+namespace lcb {
+__global__ void triu1_scale_kernel(float* A, int64_t k, float alpha) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j < k) A[i * k + j] = (j > i) ? alpha * A[i * k + j] : 0.0f;
+}
+}  // namespace lcb
+
+extern "C" int lcb_gptaq_p(float* P, float* dxxt, const float* U, int64_t k, float alpha, void* ws, size_t ws_bytes,
+                           void* stream) {
+  LCB_REQUIRE(P && dxxt && U && k > 0, "lcb_gptaq_p: bad arguments");
+  if (ws == nullptr || ws_bytes < (size_t)(k * k) * sizeof(float)) {
+    set_error("lcb_gptaq_p: workspace of %zu bytes needed", (size_t)(k * k) * sizeof(float));
+    return LCB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* T = static_cast<float*>(ws);
+  int rc = sgemm(gemm_args(dxxt, k, U, k, T, k, (int)k, (int)k, (int)k, 1.0f, 0.0f, /*transB=*/1), st);
+  if (rc != LCB_OK) return rc;
+  dim3 g2((unsigned)ceil_div(k, 256), (unsigned)k);
+  triu1_scale_kernel<<<g2, 256, 0, st>>>(T, k, alpha);
+  LCB_LAUNCH_CHECK();
+  return sgemm(gemm_args(T, k, U, k, P, k, (int)k, (int)k, (int)k, 1.0f, 0.0f, 0), st);
+}
+
+extern "C" size_t lcb_sparsegpt_ws_bytes(int64_t n, int64_t k, int block) {
+  (void)k;
+  return (size_t)(n * block) * (2 * sizeof(float) + 1) + 256 + select_ws_bytes();
+}
+
+extern "C" int lcb_sparsegpt_update(float* W, const float* U, double sparsity, int64_t n, int64_t k, int block,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  LCB_REQUIRE(W && U && n > 0 && k > 0, "lcb_sparsegpt_update: bad arguments");
+  LCB_REQUIRE(block == BLK, "lcb_sparsegpt_update: block must be 128");
+  if (ws == nullptr || ws_bytes < lcb_sparsegpt_ws_bytes(n, k, block)) {
+    set_error("lcb_sparsegpt_update: workspace of %zu bytes needed", lcb_sparsegpt_ws_bytes(n, k, block));
+    return LCB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* Err = static_cast<float*>(ws);
+  float* metric = Err + n * BLK;
+  float* thresh = metric + n * BLK;                                 // 64 floats reserved
+  uint8_t* prune = reinterpret_cast<uint8_t*>(thresh + 64);          // [n, BLK]
+  void* sel_ws = prune + ((n * BLK + 255) / 256) * 256;
+  BlockArgs a{};
+  a.W = W; a.U = U; a.Err = Err; a.prune = prune; a.n = n; a.k = k; a.group = 0; a.G = 1;
+  a.c.f = make_fmt(LCB_E_INT8);
+  const int smem = BLK * ULD * (int)sizeof(float);
+  LCB_CUDA(cudaFuncSetAttribute(block_step_kernel<MODE_SPARSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const unsigned grid = (unsigned)ceil_div(n, ROWS_PER_CTA);
+  for (int64_t i1 = 0; i1 < k; i1 += BLK) {
+    const int64_t i2 = std::min<int64_t>(i1 + BLK, k);
+    const int count = (int)(i2 - i1);
+    const int64_t numel = n * count;
+    sparse_metric_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, st>>>(W, U, metric, n, k, i1, count);
+    LCB_LAUNCH_CHECK();
+    int64_t kth = (int64_t)((double)numel * sparsity);  // int(tmp.numel() * sparsity_ratio)
+    if (kth >= numel) kth = numel - 1;
+    int rc = select_kth_f32(metric, numel, kth, thresh, sel_ws, select_ws_bytes(), st);
+    if (rc != LCB_OK) return rc;
+    sparse_mask_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, st>>>(metric, thresh, prune, n, count);
+    LCB_LAUNCH_CHECK();
+    a.i1 = i1; a.count = count;
+    block_step_kernel<MODE_SPARSE, false><<<grid, 256, smem, st>>>(a);
+    LCB_LAUNCH_CHECK();
+    if (i2 < k) {
+      rc = sgemm(gemm_args(Err, BLK, U + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), count, -1.0f, 1.0f, 0), st);
+      if (rc != LCB_OK) return rc;
+    }
+  }
+  return LCB_OK;
+}

@@ -1,0 +1,213 @@
+"""Per-layer numerics with the reference's function signatures (drop-in for L1 of SURVEY section 1).
+
+  cache_hessian_weight / update_weight            ref: quantization/calibrations/gptq/core.py:103-119,163-281
+  cache_hessian_dxxt_weight / gptaq_update_weight ref: quantization/calibrations/gptaq/core.py:116-141,198-335
+  Wrapper / prune_weight                          ref: pruning/sparsegpt/core.py:78-101,160-228
+  cache_scalar_row / wanda_mask / ria_mask / magnitude_mask
+                                                  ref: pruning/wanda/core.py:92-126, ria/core.py:118-126,
+                                                       magnitude/core.py:38-43
+
+The host code below is glue only (tensor bookkeeping, permutation indices, dtype casts); every
+arithmetic stage runs in liblcb200.so through llm_compressor_b200.ops.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _is_conv1d(layer):
+    return type(layer).__name__ == "Conv1D"
+
+
+# ----------------------------------------------------------------------------------- hooks
+def cache_hessian_weight(m, x, y):
+    """forward hook: m.weight_quantizer.H / .nsamples running mean (ref: gptq/core.py:103-119)"""
+    q = m.weight_quantizer
+    q.nsamples = ops.hessian_accum(q.H, x[0].detach(), q.nsamples)
+
+
+def cache_hessian_dxxt_weight(m, x, y):
+    """forward hook incl. the asymmetric-calibration term (ref: gptaq/core.py:116-141)"""
+    q = m.weight_quantizer
+    q.nsamples = ops.hessian_accum(q.H, x[0].detach(), q.nsamples, dxxt=q.dXXT, x_fp=m.fp_inp[0])
+    del m.fp_inp[0]
+
+
+def cache_scalar_row(m, x, y):
+    """forward hook: running mean of squared input-channel norms (ref: wanda/core.py:92-105)"""
+    m.nsamples = ops.rownorm_accum(m.scaler_row, x[0].detach(), m.nsamples)
+
+
+# ----------------------------------------------------------------------------------- GPTQ / GPTAQ
+class Factor:
+    """Everything update_weight derives from the Hessian alone: dead columns, act-order permutation
+    and U = chol(H^-1, upper).  Linears fed by the same activations (q/k/v, gate/up) have identical
+    H, so a driver may compute one Factor per group and reuse it (the reference recomputes it per
+    Linear from identical copies, ref: gptq/core.py:121-137; gptaq shares H the same way, :143-159)."""
+
+    def __init__(self, dead, perm, invperm, col_perm, U, P, group_size):
+        self.dead, self.perm, self.invperm, self.col_perm = dead, perm, invperm, col_perm
+        self.U, self.P, self.group_size = U, P, group_size
+
+
+def factorize(H, group_size, actorder=True, percdamp=0.01, dXXT=None, alpha=0.25):
+    """Dead fix (in place on H, idempotent), act-order permutation, damped Cholesky-inverse; with
+    dXXT also GPTAQ's P.  group_size is the quantizer's value BEFORE find_params (so -1 / 0 select
+    the per-column branch, ref: gptq/core.py:171,181)."""
+    K = H.shape[0]
+    dead = ops.dead_fix(H)
+    if dXXT is not None:
+        dXXT.masked_fill_(dead.unsqueeze(0), 0)
+    per_col = group_size in (0, -1)
+    perm = invperm = col_perm = None
+    if actorder:
+        diag = torch.diag(H)
+        if per_col:
+            perm = torch.argsort(diag, descending=True)
+            col_perm = perm
+        else:
+            perm = torch.argsort(diag.reshape(-1, group_size).sum(-1), descending=True)
+            col_perm = (perm.unsqueeze(1) * group_size + torch.arange(group_size, device=perm.device)).reshape(-1)
+        invperm = torch.argsort(perm)
+    U = ops.chol_inv_upper(H, perm=col_perm, percdamp=percdamp)
+    P = None
+    if dXXT is not None:
+        if col_perm is not None:
+            dXXT = dXXT[col_perm][:, col_perm].contiguous()
+        P = ops.gptaq_p(dXXT, U, alpha)
+    return Factor(dead, perm, invperm, col_perm, U, P, group_size)
+
+
+def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, factor=None):
+    q = layer.weight_quantizer
+    W = layer.weight.data.clone()
+    if _is_conv1d(layer):
+        W = W.t()
+    W = W.float().contiguous()
+    keep = (W != 0).to(torch.uint8)
+    N, K = W.shape
+    group_size = q.group_size  # read before find_params mutates -1 (ref: gptq/core.py:171)
+
+    if factor is None:
+        H = q.H
+        dXXT = q.dXXT if alpha is not None else None
+        factor = factorize(H, group_size, actorder, percdamp, dXXT, alpha if alpha is not None else 0.25)
+    for attr in ("H", "dXXT"):
+        if hasattr(q, attr):
+            delattr(q, attr)
+    W.masked_fill_(factor.dead.unsqueeze(0), 0)
+
+    per_col = group_size in (0, -1)
+    if factor.perm is None or per_col:
+        scales, zeros = q.find_params(W)  # per-column: NOT recomputed after the permutation (ref :179-185)
+    if factor.perm is not None:
+        if per_col:
+            W = W[:, factor.perm].contiguous()
+            keep = keep[:, factor.perm].contiguous()
+        else:
+            ng = K // group_size
+            W = W.reshape(N, ng, group_size)[:, factor.perm, :].reshape(N, K).contiguous()
+            keep = keep.reshape(N, ng, group_size)[:, factor.perm, :].reshape(N, K).contiguous()
+            scales, zeros = q.find_params(W)  # static groups of the re-ordered W (ref :198)
+
+    if per_col:
+        s2 = scales.float().reshape(-1, 1).expand(N, 1).contiguous()
+        z2 = zeros.float().reshape(-1, 1).expand(N, 1).contiguous()
+        grp = -1
+    else:
+        s2 = scales.float().reshape(N, K // group_size).contiguous()
+        z2 = zeros.float().reshape(N, K // group_size).contiguous()
+        grp = group_size
+    Q = ops.gptq_block_update(q._cfg(), W, factor.U, s2, z2, keep, grp, P=factor.P, block=block_size)
+
+    if factor.perm is not None:
+        if per_col:
+            Q = Q[:, factor.invperm]
+        else:
+            Q = Q.reshape(N, K // group_size, group_size)[:, factor.invperm, :].reshape(N, K)
+    if _is_conv1d(layer):
+        Q = Q.t()
+    layer.weight.data = Q.reshape(layer.weight.shape).to(layer.weight.data.dtype)
+
+
+def update_weight(layer, device, block_size=128, percdamp=0.01, actorder=False, factor=None):
+    """ref: quantization/calibrations/gptq/core.py:163-281"""
+    _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, factor=factor)
+
+
+def gptaq_update_weight(layer, device, block_size=128, percdamp=0.01, actorder=False, alpha=0.25, factor=None):
+    """ref: quantization/calibrations/gptaq/core.py:198-335"""
+    _update_weight(layer, device, block_size, percdamp, actorder, alpha=alpha, factor=factor)
+
+
+# ----------------------------------------------------------------------------------- SparseGPT
+class Wrapper:
+    """ref: pruning/sparsegpt/core.py:78-101"""
+
+    def __init__(self, module, device):
+        self.module = module
+        columns = module.weight.shape[1]
+        self.nsamples = 0
+        self.H = torch.zeros((columns, columns), device=device)
+
+    def cache_hessian_weight(self, x, y):
+        self.nsamples = ops.hessian_accum(self.H, x[0].detach(), self.nsamples)
+
+
+def prune_weight(layer, device, sparsity_ratio, block_size=128, percdamp=0.01):
+    """ref: pruning/sparsegpt/core.py:160-228"""
+    W = layer.module.weight.data.clone()
+    W = W.float().contiguous()
+    H = layer.H
+    del layer.H
+    dead = ops.dead_fix(H)
+    W.masked_fill_(dead.unsqueeze(0), 0)
+    U = ops.chol_inv_upper(H, perm=None, percdamp=percdamp)
+    del H
+    ops.sparsegpt_update(W, U, sparsity_ratio, block=block_size)
+    layer.module.weight.data = W.reshape(layer.module.weight.shape).to(layer.module.weight.data.dtype)
+
+
+# ----------------------------------------------------------------------------------- masks
+def wanda_prune_(module, sparsity_ratio):
+    """W[mask] = 0 with the Wanda mask (ref: wanda/core.py:116-126)"""
+    W = module.weight.data
+    mask = ops.mask_wanda(W.contiguous(), module.scaler_row, sparsity_ratio)
+    if W.is_contiguous():
+        ops.apply_mask(W, mask)
+    else:
+        W[mask] = 0
+    return mask
+
+
+def ria_prune_(module, sparsity_ratio, alpha):
+    """ref: ria/core.py:118-126"""
+    W = module.weight.data
+    mask = ops.mask_ria(W.contiguous(), module.scaler_row, sparsity_ratio, alpha)
+    if W.is_contiguous():
+        ops.apply_mask(W, mask)
+    else:
+        W[mask] = 0
+    return mask
+
+
+def magnitude_prune_(module, sparsity_ratio):
+    """ref: magnitude/core.py:38-43"""
+    W = module.weight.data
+    mask = ops.mask_magnitude(W.contiguous(), sparsity_ratio)
+    if W.is_contiguous():
+        ops.apply_mask(W, mask)
+    else:
+        W[mask] = 0
+    return mask
+
+
+def find_layers(module, layers=(nn.Conv2d, nn.Linear), name=""):
+    """ref: utils/module.py:54-64"""
+    if isinstance(module, layers):
+        return {name: module}
+    res = {}
+    for name1, child in module.named_children():
+        res.update(find_layers(child, layers=layers, name=name + "." + name1 if name != "" else name1))
+    return res

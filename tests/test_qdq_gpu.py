@@ -1,0 +1,179 @@
+"""GPU parity of the fused fake-quant kernels (csrc/qdq.cu) through the module API / C ABI.
+
+Bit-exact contract: scales, zeros, codes and dequantised values equal the reference's (golden
+fixtures generated from the imported reference) and the CPU oracle's on seeded inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+import oracle as orc
+from util import n_diff, same, t_from_bits, to_f32_np
+
+pytestmark = pytest.mark.gpu
+
+QDQ, QMETA = gio.load("qdq")
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _build(cfg):
+    import llm_compressor_b200 as lc
+    return lc.FakeQuantizer.build(cfg).to(_dev())
+
+
+@pytest.mark.parametrize("case", QMETA, ids=[m[0] for m in QMETA])
+def test_golden_bit_exact(case):
+    name, cfg, shape, dn = case
+    x = t_from_bits(QDQ[name + "/x"], _dev())
+    q = _build(cfg)
+    s, z = _build(cfg).find_params(x.clone())
+    y = q(x.clone())
+    assert tuple(s.shape) == tuple(QDQ[name + "/s"].shape), (s.shape, QDQ[name + "/s"].shape)
+    assert same(to_f32_np(s), gio.bits_to_f32(QDQ[name + "/s"])), "scales"
+    assert same(to_f32_np(z), gio.bits_to_f32(QDQ[name + "/z"])), "zeros"
+    ref = gio.bits_to_f32(QDQ[name + "/y"])
+    assert y.dtype == x.dtype and tuple(y.shape) == tuple(x.shape)
+    assert same(to_f32_np(y), ref), "values: %d differ" % n_diff(to_f32_np(y), ref)
+    # forward with the parameters given reproduces the same tensor
+    y2 = _build(cfg)(x.clone(), scales=s, zeros=z)
+    assert same(to_f32_np(y2), ref)
+
+
+@pytest.mark.parametrize("fmt", ["fp4_e2m1", "fp8_e4m3", "fp8_e5m2"])
+def test_elem_core_exhaustive_bf16(fmt):
+    """Every bf16 bit pattern through the element rounding (scale 1, zero 0)."""
+    z, _ = gio.load("elem_core")
+    bits = np.arange(65536, dtype=np.uint32).astype(np.uint16).reshape(512, 128)
+    x = t_from_bits(bits, _dev())
+    q = _build(dict(type="fp", format=fmt, group_size=128, axes=-1, zero_point=False, is_profile=False))
+    one = torch.ones(512, 1, 1, dtype=torch.bfloat16, device=_dev())
+    y = q(x, scales=one, zeros=torch.zeros_like(one))
+    ref = gio.bits_to_f32(z[fmt]).reshape(512, 128)
+    assert same(to_f32_np(y), ref), n_diff(to_f32_np(y), ref)
+
+
+@pytest.mark.parametrize("fmt", ["fp4_e2m1", "fp8_e4m3", "fp8_e5m2"])
+def test_elem_core_f32(fmt):
+    z, _ = gio.load("elem_core")
+    xin = z["f32_in"]
+    n = (xin.size // 128) * 128
+    x = torch.from_numpy(xin[:n].reshape(-1, 128).copy()).to(_dev())
+    q = _build(dict(type="fp", format=fmt, group_size=128, axes=-1, zero_point=False, is_profile=False))
+    one = torch.ones(x.shape[0], 1, 1, device=_dev())
+    y = q(x, scales=one, zeros=torch.zeros_like(one))
+    assert same(to_f32_np(y), z["f32_" + fmt][:n].reshape(-1, 128))
+
+
+def _c(t, f, g, axes=-1, zp=False):
+    return dict(type=t, format=f, group_size=g, axes=axes, zero_point=zp, is_profile=False)
+
+
+BIG = [
+    ("int4_g128_zp", _c("int", "int4", 128, zp=True), (1024, 3072), torch.bfloat16),
+    ("int4_g128", _c("int", "int4", 128), (1024, 3072), torch.bfloat16),
+    ("int4_g128_f32", _c("int", "int4", 128), (512, 2048), torch.float32),
+    ("int8_g128", _c("int", "int8", 128), (1, 2048, 3072), torch.bfloat16),
+    ("int4_tok", _c("int", "int4", -1), (1, 2048, 2560), torch.bfloat16),
+    ("int8_tok_long", _c("int", "int8", -1, zp=True), (64, 10240), torch.bfloat16),
+    ("int8_tok_f32", _c("int", "int8", -1), (64, 8192), torch.float32),
+    ("int8_tok_huge", _c("int", "int8", -1), (4, 20480), torch.bfloat16),   # generic kernel (group > 16384)
+    ("int8_chan", _c("int", "int8", -2), (1024, 768), torch.bfloat16),
+    ("int8_tensor", _c("int", "int8", 0, zp=True), (512, 1000), torch.bfloat16),
+    ("int4_g128_cw", _c("int", "int4", 128, axes=-2), (1, 8, 512, 64), torch.bfloat16),
+    ("int4_g128_unaligned", _c("int", "int4", 128, zp=True), (33, 1001), torch.bfloat16),
+    ("fp8e4m3_tok", _c("fp", "fp8_e4m3", -1), (1, 512, 3072), torch.bfloat16),
+    ("fp8e5m2_g128", _c("fp", "fp8_e5m2", 128, zp=True), (512, 2048), torch.bfloat16),
+    ("fp8_tensor", _c("fp", "fp8_e4m3", 0), (256, 384), torch.float32),
+    ("mxfp4", _c("mx", "fp4_e2m1", 32), (1024, 2560), torch.bfloat16),
+    ("mxfp8", _c("mx", "fp8_e4m3", 32), (512, 2560), torch.bfloat16),
+    ("mxfp4_f32", _c("mx", "fp4_e2m1", 32), (512, 1024), torch.float32),
+    ("mxint8", _c("mx", "int8", 32), (256, 1024), torch.bfloat16),
+    ("nvfp4", _c("nvfp", "fp4_e2m1", 16), (1024, 2560), torch.bfloat16),
+    ("nvfp4_zp", _c("nvfp", "fp4_e2m1", 16, zp=True), (256, 2560), torch.bfloat16),
+    ("nvfp4_f32", _c("nvfp", "fp4_e2m1", 16), (256, 1024), torch.float32),
+    ("nvfp4_act", _c("nvfp", "fp4_e2m1", 16), (1, 1024, 2560), torch.bfloat16),
+    ("nvfp4_cw", _c("nvfp", "fp4_e2m1", 16, axes=-2), (1, 4, 256, 128), torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize("case", BIG, ids=[c[0] for c in BIG])
+def test_oracle_bit_exact_seeded(case):
+    name, cfg, shape, dtype = case
+    g = torch.Generator().manual_seed(hash(name) % 10000)
+    x = torch.randn(shape, generator=g)
+    if "tok" in name or "act" in name:
+        x = x * torch.exp(torch.randn(shape[-1], generator=g))
+    else:
+        x = 0.02 * x
+    x = x.to(dtype)
+    dt = orc.BF16 if dtype == torch.bfloat16 else orc.F32
+    ref, rs, rz, rcodes = orc.qdq(x.float().numpy(), cfg, dt, want_codes=True)
+    q = _build(cfg)
+    y, s, z, codes = q.quantize_with_codes(x.to(_dev()))
+    assert same(to_f32_np(s), rs), "scales %d" % n_diff(to_f32_np(s), rs)
+    assert same(to_f32_np(z), rz), "zeros"
+    assert same(to_f32_np(y), ref), "values: %d of %d differ" % (n_diff(to_f32_np(y), ref), ref.size)
+    if cfg["type"] == "int":
+        got = codes.cpu().numpy().view(np.int8).astype(np.float32)
+        assert np.array_equal(got, rcodes), "integer codes"
+
+
+def test_fp_codes_decode_to_grid_values():
+    """uint8 codes of the float formats decode to the oracle's unit-scale grid values."""
+    cfg = _c("mx", "fp8_e4m3", 32)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(64, 256, generator=g) * 3).to(torch.bfloat16)
+    _, _, _, rcodes = orc.qdq(x.float().numpy(), cfg, orc.BF16, want_codes=True)
+    _, _, _, codes = _build(cfg).quantize_with_codes(x.to(_dev()))
+    dec = codes.view(torch.float8_e4m3fn).float().cpu().numpy()
+    assert np.array_equal(dec, rcodes)
+    cfg = _c("nvfp", "fp4_e2m1", 16)
+    _, _, _, rcodes = orc.qdq(x.float().numpy(), cfg, orc.BF16, want_codes=True)
+    _, _, _, codes = _build(cfg).quantize_with_codes(x.to(_dev()))
+    c = codes.cpu().numpy()
+    lut = np.array([0, 0.5, 1, 1.5, 2, 3, 4, 6], np.float32)
+    dec = lut[c & 7] * np.where(c & 8, -1.0, 1.0)
+    assert np.array_equal(dec, rcodes)
+
+
+def test_blocked_api_matches_reference_shapes():
+    """find_params(already_reshaped=True) and fake_quantize() take block-shaped tensors."""
+    cfg = _c("int", "int4", 128, zp=True)
+    g = torch.Generator().manual_seed(11)
+    x = (0.02 * torch.randn(16, 512, generator=g)).to(torch.bfloat16).to(_dev())
+    q = _build(cfg)
+    s, z = q.find_params(x)
+    xb = x.reshape(16, 4, 128)
+    s2, z2 = q.find_params(xb, already_reshaped=True)
+    assert torch.equal(s, s2) and torch.equal(z, z2)
+    yb = q.fake_quantize(xb, s, z)
+    assert torch.equal(yb.reshape(16, 512), q(x))
+
+
+def test_nan_scales_raise_assertion_like_reference():
+    cfg = _c("nvfp", "fp4_e2m1", 16)
+    x = torch.zeros(8, 64, dtype=torch.bfloat16, device=_dev())  # amax 0 -> 0/0 scale
+    with pytest.raises(AssertionError):
+        _build(cfg).find_params(x)
+
+
+def test_full_size_properties():
+    """BASELINE full-size weight [8192, 3072] bf16: grid membership and per-group error bound."""
+    cfg = _c("int", "int4", 128, zp=True)
+    g = torch.Generator().manual_seed(3)
+    x = (0.02 * torch.randn(8192, 3072, generator=g)).to(torch.bfloat16).to(_dev())
+    q = _build(cfg)
+    y, s, z, codes = q.quantize_with_codes(x)
+    c = codes.view(torch.int8).float().reshape(8192, 24, 128)
+    assert c.min() >= -7 and c.max() <= 7
+    xb = x.float().reshape(8192, 24, 128)
+    err = (y.float().reshape(8192, 24, 128) - xb).abs()
+    # rounding (s/2) + zero-point rounding shifting the clip edge (s/2) + bf16 arithmetic
+    assert bool((err <= 1.01 * s.float() + 2e-2 * xb.abs()).all())
+    # the CPU oracle still finishes in seconds at this size
+    ref, _, _, _ = orc.qdq(x.float().cpu().numpy(), cfg, orc.BF16)
+    assert same(to_f32_np(y), ref)

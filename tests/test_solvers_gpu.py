@@ -1,0 +1,276 @@
+"""GPU parity of the calibration statistics (a), layer solvers (b) and masks (d) against the
+reference's outputs (tests/golden) and the CPU oracle.
+
+Contract (BASELINE.json north_star): masks bit-exact; Hessians / factors / updated weights within
+the tolerances written next to each assertion; layer-output SQNR within 0.1 dB of the reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+import oracle as orc
+from util import t_from_bits, to_f32_np
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SOLV, SMETA = gio.load("solvers")
+
+
+def _ops():
+    from llm_compressor_b200 import ops
+    return ops
+
+
+def relf(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _accumulate(Xb, Xfpb=None):
+    ops = _ops()
+    X = t_from_bits(Xb, DEV)
+    K = X.shape[-1]
+    H = torch.zeros(K, K, device=DEV)
+    D = torch.zeros(K, K, device=DEV) if Xfpb is not None else None
+    Xfp = t_from_bits(Xfpb, DEV) if Xfpb is not None else None
+    n = 0
+    for j in range(X.shape[0]):
+        n = ops.hessian_accum(H, X[j].unsqueeze(0), n, dxxt=D, x_fp=None if Xfp is None else Xfp[j])
+    return H, D
+
+
+def test_hessian_matches_reference_golden():
+    H, D = _accumulate(SOLV["X"], SOLV["Xfp"])
+    # tcgen05 accumulates the exact bf16 products in fp32 with truncation inside one MMA chain
+    # (measured bias ~ -4e-6 relative on 2048-token sums); tolerance: relF 1e-5, max-abs 1e-5 of max
+    assert relf(to_f32_np(H), SOLV["H"]) < 1e-5
+    assert np.abs(to_f32_np(H) - SOLV["H"]).max() <= 1e-5 * np.abs(SOLV["H"]).max()
+    assert relf(to_f32_np(D), SOLV["dXXT"]) < 5e-5       # dX carried as bf16 hi+lo (16 mantissa bits)
+    assert np.allclose(to_f32_np(H), to_f32_np(H).T, rtol=0, atol=1e-6 * np.abs(SOLV["H"]).max())
+
+
+@pytest.mark.parametrize("T,K", [(2048, 2048), (2048, 3072), (100, 328), (4096, 1024), (65, 8), (3000, 776)])
+def test_hessian_shapes_vs_oracle(T, K):
+    ops = _ops()
+    g = torch.Generator().manual_seed(T + K)
+    X = (torch.randn(T, K, generator=g) * torch.exp(0.5 * torch.randn(K, generator=g))).to(torch.bfloat16)
+    H = torch.full((K, K), 0.25, device=DEV)
+    Href = np.full((K, K), 0.25, np.float32)
+    n = ops.hessian_accum(H, X.to(DEV).unsqueeze(0), 3)
+    assert n == 4
+    orc.hessian_accum(Href, X.float().numpy(), 3)
+    # truncating fp32 accumulation inside the tensor core: bias grows with the chain length T/16
+    assert relf(to_f32_np(H), Href) < 1e-5 * max(1.0, T / 2048)
+
+
+def test_hessian_linearity_full_size():
+    """K = 8192 (down_proj of Llama-3.2-3B), 2 samples: H(X1) + H(X2) == H([X1; X2]) scaled."""
+    ops = _ops()
+    K, T = 8192, 2048
+    g = torch.Generator(device=DEV).manual_seed(1)
+    X = torch.randn(2 * T, K, generator=g, device=DEV).to(torch.bfloat16)
+    Ha = torch.zeros(K, K, device=DEV)
+    ops.hessian_add(Ha, X[:T].contiguous(), 1.0, 0.0)
+    ops.hessian_add(Ha, X[T:].contiguous(), 1.0, 1.0)
+    Hb = torch.zeros(K, K, device=DEV)
+    ops.hessian_add(Hb, X, 1.0, 0.0)
+    assert float((Ha - Hb).norm() / Hb.norm()) < 5e-6
+    # spot check one 128 x 256 tile against fp64
+    ref = X[:, 4096:4224].double().T @ X[:, 512:768].double()
+    assert float((Hb[4096:4224, 512:768].double() - ref).norm() / ref.norm()) < 1e-5
+
+
+def test_rownorm_vs_oracle():
+    ops = _ops()
+    z, _ = gio.load("masks")
+    X = t_from_bits(z["X"], DEV)
+    s = torch.zeros(X.shape[-1], device=DEV)
+    n = 0
+    for j in range(X.shape[0]):
+        n = ops.rownorm_accum(s, X[j].unsqueeze(0), n)
+    np.testing.assert_allclose(to_f32_np(s), z["scaler_row"], rtol=3e-6)
+
+
+def _spd(K, seed, T=None):
+    g = torch.Generator().manual_seed(seed)
+    T = T or 2 * K
+    X = (torch.randn(T, K, generator=g) * torch.exp(0.7 * torch.randn(K, generator=g))).to(torch.bfloat16).float()
+    return ((2.0 / T) * X.T @ X).contiguous()
+
+
+@pytest.mark.parametrize("K", [128, 256, 384, 1000, 2048, 3072])
+def test_chol_inv_upper(K):
+    ops = _ops()
+    H = _spd(K, K)
+    Hd = H.double() + 0.01 * torch.diag(H).double().mean() * torch.eye(K, dtype=torch.float64)
+    U = ops.chol_inv_upper(H.to(DEV), percdamp=0.01).cpu().double()
+    assert float(torch.tril(U, -1).abs().max()) == 0.0
+    # U^T U (H + damp) == I
+    resid = (U.T @ U @ Hd - torch.eye(K, dtype=torch.float64)).norm() / K ** 0.5
+    Uref = torch.linalg.cholesky(torch.linalg.inv(Hd), upper=True)
+    rel = float((U - Uref).norm() / Uref.norm())
+    # reference chain in fp32 for scale: how far is IT from fp64?
+    Uo = orc.damp_and_factor(H.numpy().copy(), 0.01).astype(np.float64)
+    rel_ref = float(np.linalg.norm(Uo - Uref.numpy()) / np.linalg.norm(Uref.numpy()))
+    print(f"K={K} resid={resid:.2e} rel={rel:.2e} reference-chain rel={rel_ref:.2e}")
+    assert resid < 1e-3
+    assert rel < max(5e-4, 3 * rel_ref)
+
+
+def test_chol_perm_and_not_spd_retry():
+    ops = _ops()
+    K = 256
+    H = _spd(K, 7)
+    perm = torch.randperm(K, generator=torch.Generator().manual_seed(0))
+    U = ops.chol_inv_upper(H.to(DEV), perm=perm.to(DEV), percdamp=0.01).cpu().double()
+    Hp = H[perm][:, perm].double()
+    Hp += 0.01 * torch.diag(H).double().mean() * torch.eye(K, dtype=torch.float64)
+    assert float((U.T @ U @ Hp - torch.eye(K, dtype=torch.float64)).norm() / K ** 0.5) < 1e-3
+    bad = -torch.eye(K)  # negative definite: never factorises -> error like torch.linalg.cholesky
+    with pytest.raises(RuntimeError):
+        ops.chol_inv_upper(bad.to(DEV), percdamp=0.01)
+
+
+class _Lin(torch.nn.Linear):
+    pass
+
+
+def _layer(W, cfg):
+    import llm_compressor_b200 as lc
+    N, K = W.shape
+    lin = _Lin(K, N, bias=False, dtype=W.dtype, device=DEV)
+    lin.weight.data = W.clone().to(DEV)
+    lin.weight_quantizer = lc.FakeQuantizer.build(cfg).to(DEV)
+    return lin
+
+
+def _sqnr_db(X, W, Wq):
+    ref = X @ W.T
+    return float(10 * np.log10((ref ** 2).sum() / max(((ref - X @ Wq.T) ** 2).sum(), 1e-30)))
+
+
+@pytest.mark.parametrize("case", SMETA, ids=[m[0] for m in SMETA])
+def test_solvers_vs_reference_golden(case):
+    from llm_compressor_b200 import solvers
+    name, cfg, kind = case
+    W = t_from_bits(SOLV[name + "/W"])
+    ref = gio.bits_to_f32(SOLV[name + "/Wnew"])
+    H = torch.from_numpy(SOLV["H"].copy()).to(DEV)
+    if kind == "sparsegpt":
+        lay = solvers.Wrapper(_Lin(W.shape[1], W.shape[0], bias=False, dtype=W.dtype, device=DEV), DEV)
+        lay.module.weight.data = W.clone().to(DEV)
+        lay.H = H
+        solvers.prune_weight(lay, DEV, 0.5)
+        got = to_f32_np(lay.module.weight.data)
+        mask_diff = float(np.mean((got == 0) != (ref == 0)))
+        print(name, "mask mismatch fraction", mask_diff)
+        assert mask_diff <= 2e-3
+    else:
+        lin = _layer(W, cfg)
+        lin.weight_quantizer.H = H
+        if kind == "gptaq":
+            lin.weight_quantizer.dXXT = torch.from_numpy(SOLV["dXXT"].copy()).to(DEV)
+            solvers.gptaq_update_weight(lin, DEV, actorder=True, alpha=0.25)
+        else:
+            solvers.update_weight(lin, DEV, actorder=True)
+        got = to_f32_np(lin.weight.data)
+    rel = relf(got, ref)
+    frac = float(np.mean(got != ref))
+    X = gio.bits_to_f32(SOLV["X"]).reshape(-1, W.shape[1]).astype(np.float64)
+    W64 = W.float().numpy().astype(np.float64)
+    d_sqnr = abs(_sqnr_db(X, W64, got.astype(np.float64)) - _sqnr_db(X, W64, ref.astype(np.float64)))
+    print(f"{name}: relF={rel:.3e} changed={frac:.3e} max-abs={np.abs(got - ref).max():.3e} dSQNR={d_sqnr:.4f} dB")
+    assert d_sqnr < 0.1            # layer-output SQNR within 0.1 dB of the reference
+    assert frac < 2e-2 and rel < 5e-2   # few one-step code flips from summation order
+
+
+@pytest.mark.parametrize("N,K,cfgname", [(1024, 2048, "int4_g128"), (512, 3072, "int4_row"), (768, 1024, "mxfp4_g32"),
+                                          (256, 1024, "nvfp4_g16"), (512, 1024, "gptaq_int4_g128")])
+def test_gptq_vs_oracle_seeded(N, K, cfgname):
+    from llm_compressor_b200 import solvers
+    cfgs = {
+        "int4_g128": dict(type="int", format="int4", group_size=128, axes=-1, zero_point=False, is_profile=False),
+        "int4_row": dict(type="int", format="int4", group_size=-1, axes=-1, zero_point=True, is_profile=False),
+        "mxfp4_g32": dict(type="mx", format="fp4_e2m1", group_size=32, axes=-1, zero_point=False, is_profile=False),
+        "nvfp4_g16": dict(type="nvfp", format="fp4_e2m1", group_size=16, axes=-1, zero_point=False, is_profile=False),
+    }
+    gptaq = cfgname.startswith("gptaq_")
+    cfg = cfgs[cfgname[6:] if gptaq else cfgname]
+    g = torch.Generator().manual_seed(N + K)
+    W = (0.02 * torch.randn(N, K, generator=g)).to(torch.bfloat16)
+    T = 1024
+    chan = torch.exp(0.8 * torch.randn(K, generator=g))
+    X = (torch.randn(T, K, generator=g) * chan).to(torch.bfloat16)
+    Xfp = (X.float() + 0.05 * torch.randn(T, K, generator=g) * chan).to(torch.bfloat16)
+    H = np.zeros((K, K), np.float32); D = np.zeros((K, K), np.float32)
+    orc.hessian_accum(H, X.float().numpy(), 0, dXXT=D, x_fp=Xfp.float().numpy())
+    ref = orc.gptq_update(W.float().numpy(), H.copy(), cfg, dXXT=D.copy() if gptaq else None)
+    lin = _layer(W, cfg)
+    lin.weight_quantizer.H = torch.from_numpy(H.copy()).to(DEV)
+    if gptaq:
+        lin.weight_quantizer.dXXT = torch.from_numpy(D.copy()).to(DEV)
+        solvers.gptaq_update_weight(lin, DEV, actorder=True, alpha=0.25)
+    else:
+        solvers.update_weight(lin, DEV, actorder=True)
+    got = to_f32_np(lin.weight.data)
+    X64 = X.float().numpy().astype(np.float64); W64 = W.float().numpy().astype(np.float64)
+    d_sqnr = abs(_sqnr_db(X64, W64, got.astype(np.float64)) - _sqnr_db(X64, W64, ref.astype(np.float64)))
+    frac = float(np.mean(got != ref))
+    print(f"{cfgname} {N}x{K}: relF={relf(got, ref):.3e} changed={frac:.3e} dSQNR={d_sqnr:.4f} dB")
+    assert d_sqnr < 0.1
+    assert frac < 2e-2
+
+
+def test_sparsegpt_vs_oracle_seeded():
+    from llm_compressor_b200 import solvers
+    N, K, T = 768, 1024, 1024
+    g = torch.Generator().manual_seed(77)
+    W = (0.02 * torch.randn(N, K, generator=g)).to(torch.bfloat16)
+    X = (torch.randn(T, K, generator=g) * torch.exp(0.8 * torch.randn(K, generator=g))).to(torch.bfloat16)
+    H = np.zeros((K, K), np.float32)
+    orc.hessian_accum(H, X.float().numpy(), 0)
+    ref = orc.sparsegpt_prune(W.float().numpy(), H.copy(), 0.5)
+    lay = solvers.Wrapper(_Lin(K, N, bias=False, dtype=W.dtype, device=DEV), DEV)
+    lay.module.weight.data = W.clone().to(DEV)
+    lay.H = torch.from_numpy(H.copy()).to(DEV)
+    solvers.prune_weight(lay, DEV, 0.5)
+    got = to_f32_np(lay.module.weight.data)
+    sp = float(np.mean(got == 0))
+    mm = float(np.mean((got == 0) != (ref == 0)))
+    print(f"sparsity={sp:.4f} mask mismatch={mm:.3e} relF={relf(got, ref):.3e}")
+    assert abs(sp - 0.5) < 2e-3
+    assert mm < 5e-3
+
+
+def test_masks_bit_exact_vs_reference_golden():
+    ops = _ops()
+    z, _ = gio.load("masks")
+    W = t_from_bits(z["W"], DEV)
+    s = torch.from_numpy(z["scaler_row"].copy()).to(DEV)
+    for tag, ratio in (("30", 0.3), ("50", 0.5)):
+        assert np.array_equal(ops.mask_wanda(W, s, ratio).cpu().numpy(), z["wanda_" + tag])
+        assert np.array_equal(ops.mask_magnitude(W, ratio).cpu().numpy(), z["magnitude_" + tag])
+        for alpha in (0.5, 1.0):
+            got = ops.mask_ria(W, s, ratio, alpha).cpu().numpy()
+            assert np.array_equal(got, z[f"ria_{tag}_{alpha}"]), (tag, alpha, int((got != z[f"ria_{tag}_{alpha}"]).sum()))
+
+
+@pytest.mark.parametrize("N,K", [(512, 3072), (300, 8192), (64, 1000)])
+def test_masks_vs_oracle_seeded(N, K):
+    ops = _ops()
+    g = torch.Generator().manual_seed(N * 3 + K)
+    W = (0.02 * torch.randn(N, K, generator=g)).to(torch.bfloat16)
+    W[:, 3] = 0
+    s = (torch.rand(K, generator=g) * 4 + 0.01)
+    for ratio in (0.5, 0.3):
+        ref = orc.mask_wanda(W.float().numpy(), s.numpy(), ratio)
+        got = ops.mask_wanda(W.to(DEV), s.to(DEV), ratio).cpu().numpy()
+        assert np.array_equal(got, ref)
+        assert np.all(got.sum(1) == int(K * ratio))       # exactly k per row, ties by index
+        ref, _ = orc.mask_magnitude(W.float().numpy(), ratio)
+        assert np.array_equal(ops.mask_magnitude(W.to(DEV), ratio).cpu().numpy(), ref)
+    Wd = W.clone().to(DEV)
+    m = ops.mask_wanda(Wd, s.to(DEV), 0.5)
+    ops.apply_mask(Wd, m)
+    assert float((Wd == 0).float().mean()) >= 0.5
