@@ -121,19 +121,22 @@ def run_ours(args):
 
     def make_weights(host):
         ws = []
-        gw = torch.Generator().manual_seed(1)
-        for layer in range(N_LAYERS):
+        gw = torch.Generator(device=dev).manual_seed(1)
+        for layer in range(args.layers):
             lw = {}
             for K, lins in GROUPS:
                 for name, N in lins:
-                    w = (0.02 * torch.randn(N, K, generator=gw)).to(torch.bfloat16)
-                    lw[name] = w.pin_memory() if host else w.to(dev)
+                    w = (0.02 * torch.randn(N, K, generator=gw, device=dev)).to(torch.bfloat16)
+                    if host:
+                        hw = torch.empty((N, K), dtype=torch.bfloat16, pin_memory=True)
+                        hw.copy_(w)
+                        w = hw
+                    lw[name] = w
             ws.append(lw)
         return ws
 
     weights_dev = make_weights(host=False)
-    weights_host = make_weights(host=True) if rank == 0 or world > 1 else None
-    quantizers = {}
+    weights_host = make_weights(host=True)
 
     def quantizer():
         return lc.FakeQuantizer.build(WCFG).to(dev)
@@ -148,7 +151,7 @@ def run_ours(args):
     def one_model(from_host):
         """One step. Returns the list of (start, end) CUDA events of every Hessian accumulation."""
         evs = []
-        for layer in range(N_LAYERS):
+        for layer in range(args.layers):
             src = weights_host[layer] if from_host else weights_dev[layer]
             for gi, (K, lins) in enumerate(GROUPS):
                 H = torch.zeros(K, K, device=dev)
@@ -158,14 +161,14 @@ def run_ours(args):
                 if world == 1:
                     n = 0
                     for j in my_samples:  # one hook call per calibration sample, like the reference
-                        n = ops.hessian_accum(H, X[j], n)
+                        n = ops.hessian_accum_raw(H, X[j], n)
+                    ops.hessian_finalize(H, 2.0 / n, True)
                 else:
-                    first = True
+                    n = 0
                     for j in my_samples:  # raw partial sums, reduced over NVLink, scaled once
-                        ops.hessian_add(H, X[j], 1.0, 0.0 if first else 1.0)
-                        first = False
+                        n = ops.hessian_accum_raw(H, X[j], n)
                     dist.all_reduce(H)
-                    H.mul_(2.0 / N_SAMPLES)
+                    ops.hessian_finalize(H, 2.0 / N_SAMPLES, True)
                 e1.record()
                 evs.append((e0, e1, 2.0 * SEQ_LEN * K * K * len(my_samples)))
                 fac = solvers.factorize(H, WCFG["group_size"], actorder=True, percdamp=0.01)
@@ -231,8 +234,8 @@ def run_ours(args):
         return
     peak_tf, hbm_gbs, src = peaks()
     achieved = hess_flops / (hess_ms_total * 1e-3) / 1e12
-    wbytes = sum(N * K * 2 for K, lins in GROUPS for _, N in lins) * N_LAYERS
-    cpu = cpu_baseline_sample()
+    wbytes = sum(N * K * 2 for K, lins in GROUPS for _, N in lins) * args.layers
+    cpu = cpu_baseline_sample() if not args.no_cpu_baseline else None
     out = {
         "metric": "GPTQ W4g128 sec/model (Llama-3.2-3B)", "value": ms / 1e3 / args.steps, "unit": "s/model",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -240,7 +243,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": "Llama-3.2-3B shapes (28 layers x 7 Linears), GPTQ int4-g[128]-rw act-order, "
                                "synthetic 128x2048-token bf16 activations per Linear input, random-init bf16 weights",
-                   "calibration_forwards": "outside the path (north_star)", "hessians_per_layer": 4,
+                   "calibration_forwards": "outside the path (north_star)", "layers": args.layers, "hessians_per_layer": 4,
+                   "hessian_form": "raw sums of the symmetric half per sample + one finalize (2/n, mirror) per Hessian",
                    "l2_note": "activation buffer 4.3 GB and Hessians 38-268 MB: inputs larger than L2",
                    "parallelism": "samples sharded + all-reduce(H), rows sharded + all-gather" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_ms / 1e3 / e2e_steps, "unit": "s/model", "h2d_bytes_per_step": wbytes,
@@ -290,8 +294,8 @@ def cpu_baseline_sample():
     t_chol = time.perf_counter() - t0
     t0 = time.perf_counter()
     orc.gptq_update(W, H.copy(), WCFG)
-    t_upd = time.perf_counter() - t0 - t_chol  # gptq_update = factor + block loop
-    t_upd = max(t_upd, 1e-3)
+    t_tot = time.perf_counter() - t0           # gptq_update = parameter search + factor + block loop
+    t_upd = max(t_tot - t_chol, 0.05 * t_tot)
     # extrapolation: Hessians exactly (4 per layer, 128 samples); Cholesky ~ K^3; block loop ~ N*K^2
     hess = N_LAYERS * N_SAMPLES * (3 * t_h[D_MODEL] + t_h[D_FFN])
     chol = N_LAYERS * (3 * t_chol + t_chol * (D_FFN / D_MODEL) ** 3)
@@ -335,6 +339,10 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--layers", type=int, default=N_LAYERS,
+                    help="decoder layers per step (default: the full 28-layer model; smaller only for profiling runs, "
+                         "the JSON line then says so in config.layers)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

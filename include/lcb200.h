@@ -114,13 +114,19 @@ int lcb_nvfp_global_amax(const lcb_quant_cfg* cfg, int dtype, const void* x, int
  * cache_hessian_dxxt_weight (ref: gptaq/core.py:116-141):
  *     H = beta*H + alpha * X^T X          dXXT = beta*dXXT + alpha * (X_fp - X)^T X
  * X, X_fp: [tokens, k] bf16 row-major (token-major, as the hook receives them).
- * H, dXXT: [k, k] float32.  The hook semantics are beta = n/(n+1), alpha = 2/(n+1); a
- * token-sharded rank passes beta = 1, alpha = 1 and scales once after the all-reduce.
- * Requires k % 8 == 0.  Tensor-core path: tcgen05 (bf16 x bf16 -> fp32 in TMEM).
+ * H, dXXT: [k, k] float32.  The reference's hook is beta = n/(n+1), alpha = 2/(n+1) (running
+ * mean).  The faster equivalent keeps raw sums: beta = 1, alpha = 1 on every call and ONE
+ * lcb_hessian_finalize(scale = 2/n) before the solver; with upper_only != 0 (requires beta == 1)
+ * only the tiles touching the upper triangle of the symmetric X^T X are computed and
+ * lcb_hessian_finalize(symmetric_from_upper = 1) mirrors them.  Token-sharded ranks all-reduce the
+ * raw sums before finalising.
+ * Requires k % 8 == 0, k <= 16384.  tcgen05 path: bf16 x bf16 -> fp32 in TMEM, TMA reduce-add into H.
  */
 size_t lcb_hessian_ws_bytes(int64_t tokens, int64_t k);
 int lcb_hessian_accum(float* H, float* dxxt, const void* x, const void* x_fp, int64_t tokens, int64_t k,
-                      float alpha, float beta, void* ws, size_t ws_bytes, void* stream);
+                      float alpha, float beta, int upper_only, void* ws, size_t ws_bytes, void* stream);
+/* H *= scale; with symmetric_from_upper: H[i][j] = H[j][i] = scale * H[min(i,j)][max(i,j)] */
+int lcb_hessian_finalize(float* H, int64_t k, float scale, int symmetric_from_upper, void* stream);
 /* ref: wanda/core.py:92-105, ria/core.py:94-107:  s = beta*s + alpha * sum_t X[t,:]^2 */
 int lcb_rownorm_accum(float* s, const void* x, int64_t tokens, int64_t k, float alpha, float beta, void* stream);
 

@@ -9,11 +9,18 @@
 // the token axis as the reduction dimension.  TMA (128B swizzle, 64-channel x 64-token boxes)
 // stages the operands in shared memory, one elected thread issues tcgen05.mma (M=128, N=256,
 // K=16, bf16 x bf16 -> fp32) into TMEM, and four epilogue warps read the accumulator back with
-// tcgen05.ld and apply the running-mean update to H in place.  bf16 products are exact in fp32,
-// so the result differs from the reference's fp32 SGEMM only by summation order.
+// tcgen05.ld, stage it in swizzled shared memory and hand it to the TMA engine as a
+// cp.reduce.async.bulk.tensor (fp32 add performed at L2): the SMs never read H.
+// bf16 products are exact in fp32, so the result differs from the reference's fp32 SGEMM only by
+// summation order (the tensor core accumulates a 2048-token chain with truncation: measured
+// bias ~ -4e-6 relative).
 //
-// Persistent kernel: one CTA per SM walks the output tiles; two 256-column TMEM accumulators let
-// the epilogue of tile i overlap the MMAs of tile i+1; a 4-stage smem ring decouples TMA from MMA.
+// Scheduling: persistent stream-K.  The (tile, 64-token block) work units are split evenly over
+// one CTA per SM; because every contribution is an L2 reduce-add, a tile whose token range is cut
+// between two CTAs needs no fix-up pass.  With `upper_only` only the tiles that intersect the
+// upper triangle are computed (X^T X is symmetric; lcb_hessian_finalize mirrors and scales once).
+// Two 256-column TMEM accumulators let the epilogue of one segment overlap the MMAs of the next;
+// a 4-stage smem ring decouples TMA from MMA.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -28,13 +35,17 @@ constexpr int BKT = 64;         // tokens per pipeline stage
 constexpr int UMMA_K = 16;      // tokens per tcgen05.mma (bf16)
 constexpr int STAGES = 4;
 constexpr int BOX_C = 64;       // channels per TMA box (64 * 2 B = one 128 B swizzle row)
-constexpr int BOX_BYTES = BOX_C * BKT * 2;          // 8192
+constexpr int BOX_BYTES = BOX_C * BKT * 2;               // 8192
 constexpr int A_STAGE_BYTES = (BM / BOX_C) * BOX_BYTES;  // 16384
 constexpr int B_STAGE_BYTES = (BN / BOX_C) * BOX_BYTES;  // 32768
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int OUT_BOX = 32;                              // 32 x 32 fp32 store box (128 B rows)
+constexpr int OUT_BUF_BYTES = OUT_BOX * OUT_BOX * 4;     // 4096
+constexpr int OUT_BYTES = 4 * 2 * OUT_BUF_BYTES;         // 4 epilogue warps x double buffer
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 256 + 1024;  // + barriers + alignment slack
 constexpr int NUM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int TMEM_COLS = 512;    // two accumulators of BN fp32 columns
+constexpr int MAX_TILES_M = 128;  // k <= 16384
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -64,6 +75,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -117,33 +134,52 @@ constexpr uint32_t make_idesc() {
 }
 
 struct HessArgs {
-  float* H;
   int64_t k;       // channels
   int64_t tokens;
-  float alpha, beta;
+  float alpha;
   int tiles_m, tiles_n;
+  int num_tiles;   // computed tiles
+  int kblocks;     // 64-token blocks per tile
+  int upper_only;
+  int16_t row_start[MAX_TILES_M + 1];  // prefix sum of computed tiles per tile row
 };
 
+// linear computed-tile index -> (m0, n0)
+__device__ __forceinline__ void tile_coords(const HessArgs& a, int tile, int& m0, int& n0) {
+  int lo = 0, hi = a.tiles_m;  // largest mt with row_start[mt] <= tile
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a.row_start[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const int first_nt = a.upper_only ? (lo * BM) / BN : 0;
+  m0 = lo * BM;
+  n0 = (first_nt + (tile - a.row_start[lo])) * BN;
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, HessArgs a) {
+hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_h, const __grid_constant__ HessArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                  // [STAGES]   TMA -> MMA
-  uint64_t* empty = bars + STAGES;        // [STAGES]   MMA -> TMA
-  uint64_t* tfull = bars + 2 * STAGES;    // [2]        MMA -> epilogue
-  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
+  uint8_t* smem_out = smem + STAGES * STAGE_BYTES;  // 1024-aligned: [warp 0..3][buf 0..1][4096]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + OUT_BYTES);
+  uint64_t* full = bars;                     // [STAGES]   TMA -> MMA
+  uint64_t* empty = bars + STAGES;           // [STAGES]   MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;       // [2]        MMA -> epilogue
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = a.tiles_m * a.tiles_n;
-  const int kblocks = (int)((a.tokens + BKT - 1) / BKT);
+  // stream-K: this CTA owns the work units [u0, u1) of the (tile, token block) space
+  const int64_t units = (int64_t)a.num_tiles * a.kblocks;
+  const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_h)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -163,9 +199,13 @@ hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+      for (int64_t u = u0; u < u1;) {
+        const int tile = (int)(u / a.kblocks);
+        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
+        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+        int m0, n0;
+        tile_coords(a, tile, m0, n0);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
@@ -176,6 +216,7 @@ hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int h = 0; h < BN / BOX_C; ++h) tma_load_2d(&map_b, &full[stage], sb + h * BOX_BYTES, n0 + h * BOX_C, kb * BKT);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
@@ -185,13 +226,16 @@ hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      for (int64_t u = u0; u < u1; ++iter) {
+        const int tile = (int)(u / a.kblocks);
+        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
+        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
@@ -201,52 +245,66 @@ hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // 16 tokens = 16 swizzled rows of 128 B = 2048 B further into each 64-channel box
             const uint64_t da = make_desc(sa + k * UMMA_K * 128);
             const uint64_t db = make_desc(sb + k * UMMA_K * 128);
-            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+          if (kb == kb1 - 1) umma_commit(&tfull[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        u += kb1 - kb0;
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> H (in place) =====================
+    // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA reduce-add into H
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    uint8_t* obuf = smem_out + (warp - 2) * 2 * OUT_BUF_BYTES;
+    int iter = 0, nstore = 0;
+    for (int64_t u = u0; u < u1; ++iter) {
+      const int tile = (int)(u / a.kblocks);
+      const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
+      const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
+      int m0, n0;
+      tile_coords(a, tile, m0, n0);
       mbar_wait(&tfull[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      const int row0 = m0 + q * 32;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        // skip boxes outside the matrix and (symmetric mode) boxes entirely below the diagonal
+        const bool live = row0 < a.k && col0 < a.k && !(a.upper_only && col0 + 31 < row0);
+        if (!live) continue;  // warp-uniform
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-        const int64_t col0 = (int64_t)n0 + c * 32;
-        if (row < a.k && col0 < a.k) {
-          float* hp = a.H + row * a.k + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < a.k) {  // k % 8 == 0: a float4 is entirely in or out
-              float4 o;
-              if (a.beta != 0.0f) {
-                const float4 old = *reinterpret_cast<const float4*>(hp + j);
-                o.x = fmaf(a.alpha, v[j + 0], a.beta * old.x); o.y = fmaf(a.alpha, v[j + 1], a.beta * old.y);
-                o.z = fmaf(a.alpha, v[j + 2], a.beta * old.z); o.w = fmaf(a.alpha, v[j + 3], a.beta * old.w);
-              } else {
-                o.x = a.alpha * v[j + 0]; o.y = a.alpha * v[j + 1]; o.z = a.alpha * v[j + 2]; o.w = a.alpha * v[j + 3];
-              }
-              *reinterpret_cast<float4*>(hp + j) = o;
-            }
-          }
+        uint8_t* buf = obuf + (nstore & 1) * OUT_BUF_BYTES;
+        if (nstore >= 2) {  // the store issued two boxes ago has finished reading this buffer
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
         }
+        // row `lane` of the box, 128 B, 16-byte chunks XOR-swizzled with (row & 7) (SWIZZLE_128B)
+        uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 o = make_float4(a.alpha * v[4 * j], a.alpha * v[4 * j + 1], a.alpha * v[4 * j + 2],
+                                       a.alpha * v[4 * j + 3]);
+          *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&map_h, buf, col0, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++nstore;
       }
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      u += kb1 - kb0;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -266,6 +324,41 @@ __global__ void dx_split_kernel(const __nv_bfloat16* __restrict__ xfp, const __n
     const __nv_bfloat16 h = __float2bfloat16_rn(d);
     hi[i] = h;
     lo[i] = __float2bfloat16_rn(__fsub_rn(d, __bfloat162float(h)));
+  }
+}
+
+__global__ void scale_kernel(float* __restrict__ p, int64_t n, float s) {
+  const int64_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = p4[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    p4[i] = v;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] *= s;
+}
+
+// H[i][j] = H[j][i] = scale * S[min(i,j)][max(i,j)]   (S: upper-triangle raw sums, in place)
+__global__ void finalize_sym_kernel(float* __restrict__ H, int64_t k, float scale) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;  // one CTA per upper 32x32 block
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = (int64_t)bi * 32 + r, j = (int64_t)bj * 32 + tx;
+    float v = 0.f;
+    if (i < k && j < k) {
+      v = scale * H[i * k + j];
+      if (bi != bj || tx >= r) H[i * k + j] = v;
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    // mirrored element (j, i): row bj*32 + r, column bi*32 + tx  <- tile[tx][r]
+    const int64_t jj = (int64_t)bj * 32 + r, ii = (int64_t)bi * 32 + tx;
+    if (jj < k && ii < k && (bi != bj ? true : tx < r)) H[jj * k + ii] = tile[tx][r];
   }
 }
 
@@ -335,24 +428,65 @@ int make_x_map(CUtensorMap* map, const void* x, int64_t tokens, int64_t k) {
   return LCB_OK;
 }
 
-int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens, int64_t k, float alpha, float beta,
+// [k, k] fp32 row-major -> 2D map with 32 x 32 boxes (128 B rows, 128B swizzle) for the reduce-add
+int make_h_map(CUtensorMap* map, float* h, int64_t k) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc != LCB_OK) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)k};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 4};
+  cuuint32_t box[2] = {OUT_BOX, OUT_BOX};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (H) failed with CUresult %d (h=%p k=%lld)", (int)r, (void*)h, (long long)k);
+    return LCB_ERR_CUDA;
+  }
+  return LCB_OK;
+}
+
+// out += alpha * A_src^T B_src over the tokens; upper_only: only tiles touching the upper triangle
+int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens, int64_t k, float alpha, int upper_only,
                cudaStream_t st) {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_h;
   int rc = make_x_map(&map_a, a_src, tokens, k);
   if (rc != LCB_OK) return rc;
   rc = make_x_map(&map_b, b_src, tokens, k);
   if (rc != LCB_OK) return rc;
+  rc = make_h_map(&map_h, out, k);
+  if (rc != LCB_OK) return rc;
   HessArgs a{};
-  a.H = out; a.k = k; a.tokens = tokens; a.alpha = alpha; a.beta = beta;
+  a.k = k; a.tokens = tokens; a.alpha = alpha; a.upper_only = upper_only;
   a.tiles_m = (int)ceil_div(k, BM); a.tiles_n = (int)ceil_div(k, BN);
-  static bool attr = false;
-  if (!attr) {
-    LCB_CUDA(cudaFuncSetAttribute(hessian_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
+  if (a.tiles_m > MAX_TILES_M) {
+    set_error("lcb_hessian_accum: k = %lld is larger than the supported 16384", (long long)k);
+    return LCB_ERR_UNSUPPORTED;
   }
-  const int tiles = a.tiles_m * a.tiles_n;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  hessian_umma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, a);
+  int acc = 0;
+  for (int mt = 0; mt < a.tiles_m; ++mt) {
+    a.row_start[mt] = (int16_t)acc;
+    const int first_nt = upper_only ? (mt * BM) / BN : 0;
+    acc += a.tiles_n - first_nt;
+  }
+  a.row_start[a.tiles_m] = (int16_t)acc;
+  a.num_tiles = acc;
+  a.kblocks = (int)ceil_div(tokens, BKT);
+  LCB_CUDA(cudaFuncSetAttribute(hessian_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int64_t units = (int64_t)a.num_tiles * a.kblocks;
+  // one CTA per SM; never less than ~8 token blocks per CTA so the epilogue stays amortised
+  int grid = sm_count();
+  const int64_t cap = units / 8 > 0 ? units / 8 : 1;
+  if (grid > cap) grid = (int)cap;
+  hessian_umma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_h, a);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+int scale_inplace(float* p, int64_t n, float s, cudaStream_t st) {
+  int64_t g = ceil_div(n, 256 * 16);
+  if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
+  scale_kernel<<<(unsigned)(g < 1 ? 1 : g), 256, 0, st>>>(p, n, s);
   LCB_LAUNCH_CHECK();
   return LCB_OK;
 }
@@ -363,27 +497,33 @@ int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens,
 
 using namespace lcb;
 
-extern "C" size_t lcb_hessian_ws_bytes(int64_t tokens, int64_t k) { return (size_t)(tokens * k) * 2 * 2 + 256; }
+extern "C" size_t lcb_hessian_ws_bytes(int64_t tokens, int64_t k) { return (size_t)(tokens * k) * 2 * 2 + 512; }
 
 extern "C" int lcb_hessian_accum(float* H, float* dxxt, const void* x, const void* x_fp, int64_t tokens, int64_t k,
-                                 float alpha, float beta, void* ws, size_t ws_bytes, void* stream) {
+                                 float alpha, float beta, int upper_only, void* ws, size_t ws_bytes, void* stream) {
   LCB_REQUIRE(H != nullptr && x != nullptr, "lcb_hessian_accum: NULL pointer");
   LCB_REQUIRE(tokens > 0 && k > 0 && k % 8 == 0, "lcb_hessian_accum: need tokens > 0 and k a positive multiple of 8");
   LCB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0,
               "lcb_hessian_accum: x and H must be 16-byte aligned");
   LCB_REQUIRE((dxxt == nullptr) == (x_fp == nullptr), "lcb_hessian_accum: dxxt and x_fp go together");
+  LCB_REQUIRE(!upper_only || beta == 1.0f, "lcb_hessian_accum: upper_only accumulates raw sums (beta must be 1)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = launch_xtx(H, x, x, tokens, k, alpha, beta, st);
+  int rc;
+  if (beta != 1.0f) {  // running-mean form: scale first, every contribution below is an L2 reduce-add
+    rc = scale_inplace(H, k * k, beta, st);
+    if (rc != LCB_OK) return rc;
+  }
+  rc = launch_xtx(H, x, x, tokens, k, alpha, upper_only, st);
   if (rc != LCB_OK) return rc;
   if (dxxt != nullptr) {
     if (ws == nullptr || ws_bytes < lcb_hessian_ws_bytes(tokens, k)) {
       set_error("lcb_hessian_accum: workspace of %zu bytes needed for the dXXT term", lcb_hessian_ws_bytes(tokens, k));
       return LCB_ERR_WORKSPACE;
     }
-    LCB_REQUIRE((reinterpret_cast<uintptr_t>(x_fp) & 15) == 0 && (reinterpret_cast<uintptr_t>(dxxt) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(ws) & 255) == 0,
-                "lcb_hessian_accum: x_fp, dxxt (16 B) and ws (256 B) must be aligned");
-    __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(ws);
+    LCB_REQUIRE((reinterpret_cast<uintptr_t>(x_fp) & 15) == 0 && (reinterpret_cast<uintptr_t>(dxxt) & 15) == 0,
+                "lcb_hessian_accum: x_fp and dxxt must be 16-byte aligned");
+    uintptr_t wsa = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(wsa);
     __nv_bfloat16* lo = hi + ((tokens * k + 127) / 128) * 128;
     const int64_t n = tokens * k;
     int64_t g = ceil_div(n, 256 * 4);
@@ -391,11 +531,25 @@ extern "C" int lcb_hessian_accum(float* H, float* dxxt, const void* x, const voi
     dx_split_kernel<<<(unsigned)g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_fp),
                                                   static_cast<const __nv_bfloat16*>(x), hi, lo, n);
     LCB_LAUNCH_CHECK();
-    rc = launch_xtx(dxxt, hi, x, tokens, k, alpha, beta, st);
+    if (beta != 1.0f) {
+      rc = scale_inplace(dxxt, k * k, beta, st);
+      if (rc != LCB_OK) return rc;
+    }
+    rc = launch_xtx(dxxt, hi, x, tokens, k, alpha, 0, st);
     if (rc != LCB_OK) return rc;
-    rc = launch_xtx(dxxt, lo, x, tokens, k, alpha, 1.0f, st);
+    rc = launch_xtx(dxxt, lo, x, tokens, k, alpha, 0, st);
     if (rc != LCB_OK) return rc;
   }
+  return LCB_OK;
+}
+
+extern "C" int lcb_hessian_finalize(float* H, int64_t k, float scale, int symmetric_from_upper, void* stream) {
+  LCB_REQUIRE(H != nullptr && k > 0, "lcb_hessian_finalize: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!symmetric_from_upper) return scale_inplace(H, k * k, scale, st);
+  dim3 grid((unsigned)ceil_div(k, 32), (unsigned)ceil_div(k, 32));
+  finalize_sym_kernel<<<grid, 256, 0, st>>>(H, k, scale);
+  LCB_LAUNCH_CHECK();
   return LCB_OK;
 }
 

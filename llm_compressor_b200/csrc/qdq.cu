@@ -5,6 +5,9 @@
 //
 // Replaces ref: quantizers/{int,fp,mx,nvfp}_quant.py find_params/forward/fake_quantize and
 // quantizers/utils.py _reshape_to_blocks/_undo_reshape_to_blocks/_quantize_elemwise_core.
+#include <type_traits>
+
+#include "qdq_fast.cuh"
 #include "qmath.cuh"
 
 namespace lcb {
@@ -225,6 +228,193 @@ __global__ void __launch_bounds__(256) qdq_rowcta_kernel(QdqArgs a, uint32_t* am
       }
     }
     __syncthreads();  // bc / red reuse
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Fast variants of kernels A and B for bf16 tensors without code output (qdq_fast.cuh): same
+// results, ~5x fewer instructions per element, two independent 16 B loads in flight per lane.
+template <int KIND, int LPG>
+__global__ void __launch_bounds__(256) qdq_subwarp_fast_kernel(QdqArgs a) {
+  constexpr int VEC = 8;
+  constexpr int GPW = 32 / LPG;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPG, sl = lane % LPG;
+  const int64_t total = a.nrows * a.G;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a.x);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+  __nv_bfloat16* sc = static_cast<__nv_bfloat16*>(a.scales);
+  __nv_bfloat16* zr = static_cast<__nv_bfloat16*>(a.zeros);
+  const bool zp = a.c.zero_point != 0;
+  const bool even = a.cols == a.G * a.group;
+  float nv_g = 0.0f;
+  if (a.c.qtype == LCB_Q_NVFP && a.find) nv_g = *a.nv_amax;
+
+  for (int64_t g0 = warp * GPW * 2; g0 < total; g0 += nwarps * GPW * 2) {
+    int64_t gid[2], off[2];
+    bool active[2], inb[2];
+    uint4 v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      gid[u] = g0 + u * GPW + sub;
+      active[u] = gid[u] < total;
+      if (even) {  // cols == G * group: groups tile the tensor, no 64-bit division needed
+        inb[u] = active[u];
+        off[u] = gid[u] * a.group + (int64_t)sl * VEC;
+      } else {
+        const int64_t r = active[u] ? gid[u] / a.G : 0;
+        const int64_t b = active[u] ? gid[u] - r * a.G : 0;
+        const int64_t col = b * a.group + (int64_t)sl * VEC;
+        inb[u] = active[u] && col < a.cols;
+        off[u] = r * a.cols + col;
+      }
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (inb[u]) v[u] = *reinterpret_cast<const uint4*>(x + off[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float s, z;
+      if (a.find) {
+        Stat2 st = stats8(v[u], zp);
+#pragma unroll
+        for (int o = 1; o < LPG; o <<= 1) stat_shfl_xor(st, o, zp);
+        float mx, mn, amax;
+        stat_finish(st, zp, mx, mn, amax);
+        if constexpr (KIND == FK_INT4 || KIND == FK_INT8) int_params_fast(mx, mn, amax, zp, a.c.f, s, z);
+        else find_params<LCB_BF16, LCB_BF16>(a.c, mx, mn, amax, nv_g, s, z);
+        if (active[u] && sl == 0) {
+          flag_nan_scale(a, s);
+          if (sc != nullptr) sc[gid[u]] = __float2bfloat16_rn(s);
+          if (zr != nullptr) zr[gid[u]] = __float2bfloat16_rn(z);
+        }
+      } else {
+        s = active[u] ? __bfloat162float(sc[gid[u]]) : 1.0f;
+        z = active[u] ? __bfloat162float(zr[gid[u]]) : 0.0f;
+      }
+      if (a.apply && inb[u]) {
+        const uint4 o4 = apply8<KIND>(v[u], s, z, rcp_fast(s), zp);
+        *reinterpret_cast<uint4*>(out + off[u]) = o4;
+      }
+    }
+  }
+}
+
+
+// NVFP pass 1 (whole-tensor amax of the block statistics), bf16, groups tiling the tensor.
+template <int LPG>
+__global__ void __launch_bounds__(256) nvfp_amax_fast_kernel(QdqArgs a, uint32_t* amax_key) {
+  constexpr int VEC = 8;
+  constexpr int GPW = 32 / LPG;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPG, sl = lane % LPG;
+  const int64_t total = a.nrows * a.G;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a.x);
+  const bool zp = a.c.zero_point != 0;
+  float local = 0.0f;
+  for (int64_t g0 = warp * GPW * 2; g0 < total; g0 += nwarps * GPW * 2) {
+    uint4 v[2];
+    bool active[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t gid = g0 + u * GPW + sub;
+      active[u] = gid < total;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (active[u]) v[u] = *reinterpret_cast<const uint4*>(x + gid * a.group + (int64_t)sl * VEC);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Stat2 st = stats8(v[u], zp);
+#pragma unroll
+      for (int o = 1; o < LPG; o <<= 1) stat_shfl_xor(st, o, zp);
+      float mx, mn, amax, vb, zb;
+      stat_finish(st, zp, mx, mn, amax);
+      nvfp_block_stat<LCB_BF16>(mx, mn, amax, a.c.zero_point, vb, zb);
+      if (active[u]) local = fmaxf(local, fabsf(vb));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local = fmaxf(local, __shfl_xor_sync(0xffffffffu, local, o));
+  if (lane == 0) atomicMax(amax_key, __float_as_uint(local));
+}
+
+template <int KIND, int UNR>
+__global__ void __launch_bounds__(256) qdq_rowcta_fast_kernel(QdqArgs a) {
+  constexpr int VEC = 8;
+  __shared__ uint32_t red[2][8];
+  __shared__ float bc[2];
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a.x);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+  __nv_bfloat16* sc = static_cast<__nv_bfloat16*>(a.scales);
+  __nv_bfloat16* zr = static_cast<__nv_bfloat16*>(a.zeros);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t total = a.nrows * a.G;
+  const bool zp = a.c.zero_point != 0;
+  float nv_g = 0.0f;
+  if (a.c.qtype == LCB_Q_NVFP && a.find) nv_g = *a.nv_amax;
+
+  for (int64_t gid = blockIdx.x; gid < total; gid += gridDim.x) {
+    const int64_t r = gid / a.G, b = gid - r * a.G;
+    const int64_t c0 = b * a.group;
+    const int64_t glen = min(a.group, a.cols - c0);
+    uint4 v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t e = ((int64_t)u * 256 + tid) * VEC;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (e < glen) v[u] = *reinterpret_cast<const uint4*>(x + r * a.cols + c0 + e);
+    }
+    float s, z;
+    if (a.find) {
+      Stat2 st = stats8(v[0], zp);  // thread 0..: e = tid*8 < group always holds for u == 0 when group >= 2048
+#pragma unroll
+      for (int u = 1; u < UNR; ++u) {
+        const int64_t e = ((int64_t)u * 256 + tid) * VEC;
+        if (e < a.group) { Stat2 t = stats8(v[u], zp); stat_combine(st, t, zp); }
+      }
+      // threads entirely beyond a short group hold zeros = the padding value only if the group is ragged;
+      // for a group shorter than 2048 elements that is not ragged they must not contribute
+      if ((int64_t)tid * VEC >= a.group) { st.mxmn = 0xff80ff80u; st.amax = 0; }  // (-inf, -inf) / 0
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) stat_shfl_xor(st, o, zp);
+      if (lane == 0) { red[0][wid] = st.mxmn; red[1][wid] = st.amax; }
+      __syncthreads();
+      if (wid == 0) {
+        Stat2 t;
+        t.mxmn = lane < 8 ? red[0][lane] : 0xff80ff80u;
+        t.amax = lane < 8 ? red[1][lane] : 0u;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) stat_shfl_xor(t, o, zp);
+        if (lane == 0) {
+          float mx, mn, amax;
+          stat_finish(t, zp, mx, mn, amax);
+          if constexpr (KIND == FK_INT4 || KIND == FK_INT8) int_params_fast(mx, mn, amax, zp, a.c.f, s, z);
+          else find_params<LCB_BF16, LCB_BF16>(a.c, mx, mn, amax, nv_g, s, z);
+          flag_nan_scale(a, s);
+          if (sc != nullptr) sc[gid] = __float2bfloat16_rn(s);
+          if (zr != nullptr) zr[gid] = __float2bfloat16_rn(z);
+          bc[0] = s; bc[1] = z;
+        }
+      }
+      __syncthreads();
+      s = bc[0]; z = bc[1];
+    } else {
+      s = __bfloat162float(sc[gid]);
+      z = __bfloat162float(zr[gid]);
+    }
+    if (a.apply) {
+      const float rr = rcp_fast(s);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t e = ((int64_t)u * 256 + tid) * VEC;
+        if (e < glen) *reinterpret_cast<uint4*>(out + r * a.cols + c0 + e) = apply8<KIND>(v[u], s, z, rr, zp);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -461,6 +651,60 @@ static int grid_for(int64_t work_items, int64_t items_per_cta, int ctas_per_sm) 
   return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
+
+// which fast path (qdq_fast.cuh) covers this configuration; -1 = generic kernels
+static int fast_kind(const QdqArgs& a) {
+  if (a.codes != nullptr) return -1;
+  if (a.c.qtype == LCB_Q_INT) return a.c.f.mbits == 4 ? FK_INT4 : FK_INT8;
+  if (a.c.f.ebits == 0) return -1;  // MX with integer elements
+  return a.c.f.ebits == 2 ? FK_E2M1 : (a.c.f.ebits == 4 ? FK_E4M3 : FK_E5M2);
+}
+
+template <int KIND>
+static int launch_subwarp_fast_k(const QdqArgs& a, int lpg, int64_t total, cudaStream_t st) {
+  const int gpw = 32 / lpg;
+  const int grid = grid_for(total, (int64_t)8 * gpw * 2, 8);
+  switch (lpg) {
+    case 1: qdq_subwarp_fast_kernel<KIND, 1><<<grid, 256, 0, st>>>(a); break;
+    case 2: qdq_subwarp_fast_kernel<KIND, 2><<<grid, 256, 0, st>>>(a); break;
+    case 4: qdq_subwarp_fast_kernel<KIND, 4><<<grid, 256, 0, st>>>(a); break;
+    case 8: qdq_subwarp_fast_kernel<KIND, 8><<<grid, 256, 0, st>>>(a); break;
+    case 16: qdq_subwarp_fast_kernel<KIND, 16><<<grid, 256, 0, st>>>(a); break;
+    default: qdq_subwarp_fast_kernel<KIND, 32><<<grid, 256, 0, st>>>(a); break;
+  }
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+static int launch_subwarp_fast(const QdqArgs& a, int kind, int lpg, int64_t total, cudaStream_t st) {
+  switch (kind) {
+    case FK_INT4: return launch_subwarp_fast_k<FK_INT4>(a, lpg, total, st);
+    case FK_INT8: return launch_subwarp_fast_k<FK_INT8>(a, lpg, total, st);
+    case FK_E2M1: return launch_subwarp_fast_k<FK_E2M1>(a, lpg, total, st);
+    case FK_E4M3: return launch_subwarp_fast_k<FK_E4M3>(a, lpg, total, st);
+    default: return launch_subwarp_fast_k<FK_E5M2>(a, lpg, total, st);
+  }
+}
+template <int KIND>
+static int launch_rowcta_fast_k(const QdqArgs& a, int64_t total, cudaStream_t st) {
+  const int grid = grid_for(total, 1, 8);
+  const int64_t per = 256 * 8;
+  if (a.group <= per) qdq_rowcta_fast_kernel<KIND, 1><<<grid, 256, 0, st>>>(a);
+  else if (a.group <= 2 * per) qdq_rowcta_fast_kernel<KIND, 2><<<grid, 256, 0, st>>>(a);
+  else if (a.group <= 4 * per) qdq_rowcta_fast_kernel<KIND, 4><<<grid, 256, 0, st>>>(a);
+  else qdq_rowcta_fast_kernel<KIND, 8><<<grid, 256, 0, st>>>(a);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+static int launch_rowcta_fast(const QdqArgs& a, int kind, int64_t total, cudaStream_t st) {
+  switch (kind) {
+    case FK_INT4: return launch_rowcta_fast_k<FK_INT4>(a, total, st);
+    case FK_INT8: return launch_rowcta_fast_k<FK_INT8>(a, total, st);
+    case FK_E2M1: return launch_rowcta_fast_k<FK_E2M1>(a, total, st);
+    case FK_E4M3: return launch_rowcta_fast_k<FK_E4M3>(a, total, st);
+    default: return launch_rowcta_fast_k<FK_E5M2>(a, total, st);
+  }
+}
+
 template <typename T, bool P1>
 static int launch_rowwise(const QdqArgs& a, uint32_t* amax_key, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
@@ -469,6 +713,28 @@ static int launch_rowwise(const QdqArgs& a, uint32_t* amax_key, cudaStream_t st)
                         (a.codes ? reinterpret_cast<uintptr_t>(a.codes) : 0)) & 15) == 0;
   const bool vec_ok = ptr_ok && (a.cols % VEC == 0) && (a.group % VEC == 0);
   const int64_t lpg = a.group / VEC;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value && P1) {
+    if (vec_ok && a.cols == a.G * a.group && lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0) {
+      const int grid = grid_for(total, (int64_t)8 * (32 / (int)lpg) * 2, 8);
+      switch (lpg) {
+        case 1: nvfp_amax_fast_kernel<1><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 2: nvfp_amax_fast_kernel<2><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 4: nvfp_amax_fast_kernel<4><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 8: nvfp_amax_fast_kernel<8><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 16: nvfp_amax_fast_kernel<16><<<grid, 256, 0, st>>>(a, amax_key); break;
+        default: nvfp_amax_fast_kernel<32><<<grid, 256, 0, st>>>(a, amax_key); break;
+      }
+      LCB_LAUNCH_CHECK();
+      return LCB_OK;
+    }
+  }
+  if constexpr (std::is_same<T, __nv_bfloat16>::value && !P1) {
+    const int kind = fast_kind(a);
+    if (kind >= 0 && vec_ok) {
+      if (lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0) return launch_subwarp_fast(a, kind, (int)lpg, total, st);
+      if (a.group <= (int64_t)256 * VEC * 8) return launch_rowcta_fast(a, kind, total, st);
+    }
+  }
   if (vec_ok && lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0) {
     const int gpw = 32 / (int)lpg;
     const int grid = grid_for(total, (int64_t)8 * gpw, 8);

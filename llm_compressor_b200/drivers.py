@@ -150,19 +150,30 @@ def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, da
         full = solvers.find_layers(layer)
         for names in sequential:
             subset = {n: full[n] for n in names}
-            for name in subset:
-                columns = subset[name].weight.shape[1]
-                subset[name].weight_quantizer.mse = mse
-                subset[name].weight_quantizer.nsamples = 0
-                subset[name].weight_quantizer.H = torch.zeros((columns, columns), device=device)
-            handles = [subset[name].register_forward_hook(solvers.cache_hessian_weight) for name in subset]
+            # The Linears of one sequential group see the same input, so their Hessians are identical
+            # (the reference accumulates one copy per Linear, gptq/core.py:121-123): hook the first
+            # module only and share H, the act-order permutation and the Cholesky factor.
+            first = list(subset.keys())[0]
+            columns = subset[first].weight.shape[1]
+            fq = subset[first].weight_quantizer
+            fq.nsamples = 0
+            fq.H = torch.zeros((columns, columns), device=device)
+            handle = subset[first].register_forward_hook(solvers.cache_hessian_weight)
             for j in range(n_samples):
                 layer(inps[j].unsqueeze(0), **layer_kwargs)
-            for h in handles:
-                h.remove()
+            handle.remove()
+            H = solvers.finalize_hessian(fq)
+            factors = {}
             for name in subset:
-                solvers.update_weight(layer=subset[name], device=device, block_size=128, percdamp=0.01, actorder=True)
+                wq = subset[name].weight_quantizer
+                wq.mse = mse
+                key = wq.group_size if wq.group_size not in (0, -1) else -1
+                if key not in factors:
+                    factors[key] = solvers.factorize(H, wq.group_size, actorder=True, percdamp=0.01)
+                solvers.update_weight(layer=subset[name], device=device, block_size=128, percdamp=0.01, actorder=True,
+                                      factor=factors[key])
                 del subset[name].weight_quantizer
+            del H, factors
         for j in range(n_samples):
             outs[j] = _first(layer(inps[j].unsqueeze(0), **layer_kwargs))
         layers[i] = layer.cpu()
@@ -203,6 +214,7 @@ def gptaq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, d
             for j in range(n_samples):
                 layer(inps[j].unsqueeze(0), **layer_kwargs)
             handle.remove()
+            solvers.finalize_hessian(subset[first].weight_quantizer)
             for name in subset:  # H and dXXT are shared by the whole group (gptaq/core.py:149-159)
                 if name != first:
                     subset[name].weight_quantizer.H = subset[first].weight_quantizer.H

@@ -32,8 +32,10 @@ def _x2d(x):
     return x2.contiguous(), batch
 
 
-def hessian_add(H, x2d, alpha, beta, dxxt=None, xfp2d=None):
-    """H = beta*H + alpha*X^T X  (and dXXT likewise with (X_fp - X)^T X).  x2d: [tokens, k] bf16."""
+def hessian_add(H, x2d, alpha, beta, dxxt=None, xfp2d=None, upper_only=False):
+    """H = beta*H + alpha*X^T X  (and dXXT likewise with (X_fp - X)^T X).  x2d: [tokens, k] bf16.
+    upper_only (beta must be 1): only the tiles touching the upper triangle of H are accumulated;
+    call hessian_finalize(H, scale, symmetric=True) once at the end."""
     _need_cuda(H, x2d, dxxt, xfp2d)
     L = _lib.lib()
     tokens, k = x2d.shape
@@ -46,8 +48,26 @@ def hessian_add(H, x2d, alpha, beta, dxxt=None, xfp2d=None):
         ws = _ws(ws_bytes, H.device)
     with torch.cuda.device(H.device):
         rc = L.lcb_hessian_accum(_ptr(H), _ptr(dxxt), _ptr(x2d), _ptr(xfp2d), tokens, k, float(alpha), float(beta),
-                                 _ptr(ws), ws_bytes, _stream(H.device))
+                                 1 if upper_only else 0, _ptr(ws), ws_bytes, _stream(H.device))
     _lib.check(rc, "lcb_hessian_accum")
+
+
+def hessian_finalize(H, scale, symmetric):
+    """H *= scale, mirroring the upper triangle into the lower one when `symmetric`."""
+    _need_cuda(H)
+    with torch.cuda.device(H.device):
+        rc = _lib.lib().lcb_hessian_finalize(_ptr(H), H.shape[0], float(scale), 1 if symmetric else 0, _stream(H.device))
+    _lib.check(rc, "lcb_hessian_finalize")
+    return H
+
+
+def hessian_accum_raw(H, x, nsamples, dxxt=None, x_fp=None):
+    """Lazy form of the hook: raw sums H += X^T X (upper-triangle tiles only), dXXT += (X_fp-X)^T X.
+    Equal to the reference's running mean after hessian_finalize(H, 2/n, True)."""
+    x2d, batch = _x2d(x)
+    xfp2d = _x2d(x_fp)[0] if x_fp is not None else None
+    hessian_add(H, x2d, 1.0, 1.0, dxxt, xfp2d, upper_only=True)
+    return nsamples + batch
 
 
 def hessian_accum(H, x, nsamples, dxxt=None, x_fp=None):

@@ -21,16 +21,41 @@ def _is_conv1d(layer):
 
 
 # ----------------------------------------------------------------------------------- hooks
+# "lazy": the hooks accumulate raw sums S += X^T X (symmetric half only) and the running-mean factor
+#         2/n is applied once, by finalize_hessian(), right before the solver reads H -- algebraically the
+#         reference's H (gptq/core.py:113-119 telescopes to (2/n) * sum_j X_j^T X_j).
+# "exact": every hook call leaves H equal to the reference's running mean (beta = n/(n+1), alpha = 2/(n+1)).
+HESSIAN_MODE = "lazy"
+
+
+def _accumulate(holder, x, dxxt=None, x_fp=None):
+    if HESSIAN_MODE == "exact":
+        holder.nsamples = ops.hessian_accum(holder.H, x, holder.nsamples, dxxt=dxxt, x_fp=x_fp)
+    else:
+        holder.nsamples = ops.hessian_accum_raw(holder.H, x, holder.nsamples, dxxt=dxxt, x_fp=x_fp)
+        holder._h_raw = True
+
+
+def finalize_hessian(holder):
+    """Bring holder.H (and holder.dXXT) to the reference's running-mean value. Idempotent."""
+    if getattr(holder, "_h_raw", False):
+        scale = 2.0 / max(holder.nsamples, 1)
+        ops.hessian_finalize(holder.H, scale, True)
+        if getattr(holder, "dXXT", None) is not None:
+            ops.hessian_finalize(holder.dXXT, scale, False)
+        holder._h_raw = False
+    return holder.H
+
+
 def cache_hessian_weight(m, x, y):
-    """forward hook: m.weight_quantizer.H / .nsamples running mean (ref: gptq/core.py:103-119)"""
-    q = m.weight_quantizer
-    q.nsamples = ops.hessian_accum(q.H, x[0].detach(), q.nsamples)
+    """forward hook: m.weight_quantizer.H / .nsamples (ref: gptq/core.py:103-119)"""
+    _accumulate(m.weight_quantizer, x[0].detach())
 
 
 def cache_hessian_dxxt_weight(m, x, y):
     """forward hook incl. the asymmetric-calibration term (ref: gptaq/core.py:116-141)"""
     q = m.weight_quantizer
-    q.nsamples = ops.hessian_accum(q.H, x[0].detach(), q.nsamples, dxxt=q.dXXT, x_fp=m.fp_inp[0])
+    _accumulate(q, x[0].detach(), dxxt=q.dXXT, x_fp=m.fp_inp[0])
     del m.fp_inp[0]
 
 
@@ -90,7 +115,7 @@ def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, fa
     group_size = q.group_size  # read before find_params mutates -1 (ref: gptq/core.py:171)
 
     if factor is None:
-        H = q.H
+        H = finalize_hessian(q)
         dXXT = q.dXXT if alpha is not None else None
         factor = factorize(H, group_size, actorder, percdamp, dXXT, alpha if alpha is not None else 0.25)
     for attr in ("H", "dXXT"):
@@ -152,14 +177,14 @@ class Wrapper:
         self.H = torch.zeros((columns, columns), device=device)
 
     def cache_hessian_weight(self, x, y):
-        self.nsamples = ops.hessian_accum(self.H, x[0].detach(), self.nsamples)
+        _accumulate(self, x[0].detach())
 
 
 def prune_weight(layer, device, sparsity_ratio, block_size=128, percdamp=0.01):
     """ref: pruning/sparsegpt/core.py:160-228"""
     W = layer.module.weight.data.clone()
     W = W.float().contiguous()
-    H = layer.H
+    H = finalize_hessian(layer)
     del layer.H
     dead = ops.dead_fix(H)
     W.masked_fill_(dead.unsqueeze(0), 0)

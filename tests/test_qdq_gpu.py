@@ -177,3 +177,29 @@ def test_full_size_properties():
     # the CPU oracle still finishes in seconds at this size
     ref, _, _, _ = orc.qdq(x.float().cpu().numpy(), cfg, orc.BF16)
     assert same(to_f32_np(y), ref)
+
+
+@pytest.mark.parametrize("cfgname", ["int4", "int4_zp", "int8_zp", "fp4_zp", "fp8e4m3", "fp8e5m2_zp", "mxfp8"])
+def test_all_bf16_patterns_with_given_params_vs_oracle(cfgname):
+    """Every bf16 bit pattern (incl. NaN / inf / denormals) through fake_quantize with fixed
+    non-trivial parameters: exercises the division-free fast path against the op-by-op oracle."""
+    cfgs = {
+        "int4": (_c("int", "int4", 128), 0.046875, 0.0),
+        "int4_zp": (_c("int", "int4", 128, zp=True), 0.0390625, 3.0),
+        "int8_zp": (_c("int", "int8", 128, zp=True), 0.01171875, -19.0),
+        "fp4_zp": (_c("fp", "fp4_e2m1", 128, zp=True), 0.7265625, 0.158203125),
+        "fp8e4m3": (_c("fp", "fp8_e4m3", 128), 0.00592041015625, 0.0),
+        "fp8e5m2_zp": (_c("fp", "fp8_e5m2", 128, zp=True), 3.046875, -1.2109375),
+        "mxfp8": (_c("mx", "fp8_e4m3", 32), 0.0078125, 0.0),
+    }
+    cfg, sv, zv = cfgs[cfgname]
+    g = cfg["group_size"]
+    bits = np.arange(65536, dtype=np.uint32).astype(np.uint16).reshape(-1, 128)
+    x = t_from_bits(bits, _dev())
+    G = 128 // g
+    s = torch.full((x.shape[0], G, 1), sv, dtype=torch.bfloat16, device=_dev())
+    z = torch.full((x.shape[0], G, 1), zv, dtype=torch.bfloat16, device=_dev())
+    assert float(s[0, 0, 0]) == sv and float(z[0, 0, 0]) == zv  # parameters are bf16-exact
+    y = _build(cfg)(x, scales=s, zeros=z)
+    ref, _, _, _ = orc.qdq(gio.bits_to_f32(bits), cfg, orc.BF16, scales=to_f32_np(s), zeros=to_f32_np(z))
+    assert same(to_f32_np(y), ref), n_diff(to_f32_np(y), ref)
