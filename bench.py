@@ -189,8 +189,11 @@ def run_ours(args):
                         parts = [torch.empty_like(out) for _ in range(world)]
                         dist.all_gather(parts, out.contiguous())
                         out = torch.cat(parts, 0)[:N]
-                    if from_host:
-                        weights_host[layer][name + "_out"] = out.to("cpu", non_blocking=True)
+                    if from_host:  # device -> pinned host buffer, asynchronous on the compute stream
+                        key = name + "_out"
+                        if key not in weights_host[layer]:
+                            weights_host[layer][key] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                        weights_host[layer][key].copy_(out, non_blocking=True)
         return evs
 
     def timed(from_host, steps):

@@ -17,7 +17,6 @@ namespace lcb {
 namespace {
 
 constexpr int NB = 128;
-constexpr int LDT = NB + 1;  // padded shared-memory row stride (bank-conflict free column access)
 
 // H[dead,dead] = 1 where diag(H) == 0 (ref: gptq/core.py:175-176); dead flags out.
 __global__ void dead_fix_kernel(float* H, int64_t k, uint8_t* dead) {
@@ -73,51 +72,196 @@ __global__ void zero_strict_upper_kernel(float* A, int64_t k) {
   if (j < k && j > i) A[i * k + j] = 0.0f;
 }
 
-// One CTA (128 threads): Cholesky of the nb x nb diagonal block at A (ld) in shared memory, left
-// looking, thread i owns row i.  Also the inverse of the factor (column j per thread, forward
-// substitution) to `dinv` [nb x NB], used to turn the panel TRSM into a GEMM.
-__global__ void __launch_bounds__(NB) potf2_inv_kernel(float* A, int64_t ld, int nb, float* dinv, uint32_t* status) {
-  extern __shared__ float sm[];
-  float* L = sm;             // [NB][LDT]
-  float* X = sm + NB * LDT;  // [NB][LDT]
-  const int i = threadIdx.x;
-  for (int r = 0; r < nb; ++r) L[r * LDT + i] = (i < nb && i <= r) ? A[(int64_t)r * ld + i] : 0.0f;
-  __syncthreads();
-  bool bad = false;
-  for (int j = 0; j < nb; ++j) {
-    __syncthreads();  // column j-1 (written by other threads) is visible
-    float v = 0.f;
-    if (i >= j && i < nb) {
-      v = L[i * LDT + j];
-      for (int k = 0; k < j; ++k) v = fmaf(-L[i * LDT + k], L[j * LDT + k], v);
+// One CTA (256 threads): Cholesky of the nb x nb diagonal block at A (ld) and the inverse of the
+// factor (`dinv` [NB x NB], turns the panel TRSM into a GEMM).  The 128 x 128 block lives in
+// registers, 8 x 8 per thread (thread (ty, tx) owns rows ty*8.., columns tx*8..).  Both phases are
+// blocked by 8: per panel one thread factors / inverts an 8 x 8 diagonal tile in registers, the
+// panel tiles are exchanged through shared memory and every other thread does 8x8x8 register
+// FMAs -- 16 panel steps of ~3 barriers instead of 128 latency-bound column steps.
+__global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, int nb, float* dinv, uint32_t* status) {
+  constexpr int PS = 9;                   // padded panel row stride
+  __shared__ float P[NB * PS];            // column panel  P[r][m] = L[r][p*8 + m]
+  __shared__ float XP[8 * (NB + 4)];      // row panel     XP[m][c] = X[k*8 + m][c]
+  __shared__ float dall[16][64];          // inverted diagonal tiles
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  float a[8][8], x[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      float v = (r == cc) ? 1.0f : 0.0f;  // identity padding for a short last block
+      if (r < nb && cc < nb) v = (cc <= r) ? A[(int64_t)r * ld + cc] : 0.0f;
+      a[i][c] = v;
+      x[i][c] = (r == cc) ? 1.0f : 0.0f;
     }
-    if (i == j) {
-      if (!(v > 0.0f)) bad = true;
-      L[j * LDT + j] = sqrtf(v);
+  bool bad = false;
+
+  // ================= factorisation, right-looking over 16 panels of 8 columns
+#pragma unroll 1
+  for (int p = 0; p < 16; ++p) {
+    if (ty == p && tx == p) {
+      // unblocked Cholesky of the 8 x 8 diagonal tile, then its inverse
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = a[j][j];
+        if (!(d > 0.0f)) bad = true;
+        const float l = sqrtf(d);
+        const float rl = __frcp_rn(l);
+        a[j][j] = l;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) a[i][j] *= rl;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c)
+#pragma unroll
+          for (int i = c; i < 8; ++i) a[i][c] = fmaf(-a[i][j], a[c][j], a[i][c]);
+      }
+      float di[8][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) di[i][j] = 0.0f;
+        const float rj = __frcp_rn(a[j][j]);
+        di[j][j] = rj;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int m = j; m < i; ++m) sacc = fmaf(a[i][m], di[m][j], sacc);
+          di[i][j] = -sacc * __frcp_rn(a[i][i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          dall[p][i * 8 + c] = di[i][c];
+          if (c > i) a[i][c] = 0.0f;
+        }
     }
     __syncthreads();
-    if (i > j && i < nb) L[i * LDT + j] = v / L[j * LDT + j];
+    if (tx == p && ty >= p) {
+      if (ty > p) {  // L_ip = A_ip * L_pp^-T : new[i][c] = sum_{m <= c} a[i][m] * Dinv[c][m]
+        float dv[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dv[i][c] = dall[p][i * 8 + c];
+        float nw[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m <= c; ++m) acc = fmaf(a[i][m], dv[c][m], acc);
+            nw[i][c] = acc;
+          }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[i][c] = nw[i][c];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) P[(ty * 8 + i) * PS + c] = a[i][c];
+    }
+    __syncthreads();
+    if (ty > p && tx > p && tx <= ty) {  // trailing update of the lower tiles
+      float lr[8][8], lc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          lr[i][m] = P[(ty * 8 + i) * PS + m];
+          lc[i][m] = P[(tx * 8 + i) * PS + m];
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float acc = a[i][c];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) acc = fmaf(-lr[i][m], lc[c][m], acc);
+          a[i][c] = acc;
+        }
+    }
+    // the next panel's P is written only after the next iteration's first barrier
   }
-  __syncthreads();
   if (bad && status) atomicOr(status, LCB_ST_NOT_SPD);
-  // inverse: thread j computes column j of X = L^-1
-  const int j = i;
-  if (j < nb) {
-    for (int r = 0; r < j; ++r) X[r * LDT + j] = 0.0f;
-    X[j * LDT + j] = 1.0f / L[j * LDT + j];
-    for (int r = j + 1; r < nb; ++r) {
-      float s = 0.f;
-      for (int k = j; k < r; ++k) s = fmaf(L[r * LDT + k], X[k * LDT + j], s);
-      X[r * LDT + j] = -s / L[r * LDT + r];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      if (r < nb && cc < nb) A[(int64_t)r * ld + cc] = (cc <= r) ? a[i][c] : 0.0f;
     }
-  }
   __syncthreads();
-  for (int r = 0; r < nb; ++r) {
-    if (i < nb) {
-      A[(int64_t)r * ld + i] = (i <= r) ? L[r * LDT + i] : 0.0f;
-      dinv[r * NB + i] = X[r * LDT + i];
+
+  // ================= X = L^-1, blocked forward substitution over the 16 row panels
+#pragma unroll 1
+  for (int k = 0; k < 16; ++k) {
+    if (ty == k && tx <= k) {  // row panel k becomes final: X_k,: = Dinv_k * (accumulated tile)
+      float dv[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dv[i][c] = dall[k][i * 8 + c];
+      float nw[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int m = 0; m <= i; ++m) acc = fmaf(dv[i][m], x[m][c], acc);
+          nw[i][c] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          x[i][c] = nw[i][c];
+          XP[i * (NB + 4) + tx * 8 + c] = nw[i][c];
+        }
     }
+    if (tx == k && ty > k) {  // column panel k of L below the diagonal tile
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) P[(ty * 8 + i) * PS + c] = a[i][c];
+    }
+    __syncthreads();
+    if (ty > k && tx <= k) {  // X_i,: -= L_ik * X_k,:
+      float lr[8][8], xr[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          lr[i][m] = P[(ty * 8 + i) * PS + m];
+          xr[i][m] = XP[i * (NB + 4) + tx * 8 + m];  // xr[m'][c]: row m' of the panel, columns of my tile
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float acc = x[i][c];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) acc = fmaf(-lr[i][m], xr[m][c], acc);
+          x[i][c] = acc;
+        }
+    }
+    __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      if (r < nb) dinv[r * NB + cc] = (cc <= r && cc < nb) ? x[i][c] : 0.0f;
+    }
 }
 
 // copy the inverted diagonal blocks (dinv_all: [nblk][NB][NB]) onto the diagonal of A
@@ -169,12 +313,6 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   float* panel = dinv_all + nblk * NB * NB;
   float* dsum = panel + k * NB;
 
-  static bool attr_set = false;
-  const int smem = 2 * NB * LDT * (int)sizeof(float);
-  if (!attr_set) {
-    LCB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
 
   diag_sum_kernel<<<1, 1024, 0, st>>>(H, k, dsum);
   LCB_LAUNCH_CHECK();
@@ -188,7 +326,7 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
     const int nb = (int)std::min<int64_t>(NB, k - j);
     float* Ajj = A + j * k + j;
     float* dinv = dinv_all + b * NB * NB;
-    potf2_inv_kernel<<<1, NB, smem, st>>>(Ajj, k, nb, dinv, status);
+    potf2_inv_kernel<<<1, 256, 0, st>>>(Ajj, k, nb, dinv, status);
     LCB_LAUNCH_CHECK();
     const int64_t m2 = k - j - nb;
     if (m2 <= 0) break;

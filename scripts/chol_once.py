@@ -1,0 +1,12 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from llm_compressor_b200 import ops
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 3072
+g = torch.Generator(device="cuda:0").manual_seed(0)
+X = torch.randn(2 * K, K, generator=g, device="cuda:0").to(torch.bfloat16).float()
+H = (X.T @ X / K).contiguous()
+for _ in range(2):
+    U = ops.chol_inv_upper(H, percdamp=0.01)
+torch.cuda.synchronize()
+print("ok", float(U[0, 0]))
