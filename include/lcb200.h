@@ -164,13 +164,33 @@ size_t lcb_gptq_ws_bytes(int64_t n, int64_t k, int block);
 int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, const float* U, const float* P, const float* scales,
                     const float* zeros, const uint8_t* keep, int64_t n, int64_t k, int64_t group, int block,
                     void* ws, size_t ws_bytes, void* stream);
-/* P = alpha * triu(dXXT @ U^T, 1) @ U   (ref: gptaq/core.py:272); dXXT is overwritten */
+/* P = alpha * triu(dXXT @ U^T, 1) @ U   (ref: gptaq/core.py:272); dXXT is left untouched */
+size_t lcb_gptaq_p_ws_bytes(int64_t k);
 int lcb_gptaq_p(float* P, float* dxxt, const float* U, int64_t k, float alpha, void* ws, size_t ws_bytes, void* stream);
 
 /* Block loop of sparsegpt.prune_weight (ref: sparsegpt/core.py:192-218); W [n,k] fp32 in/out. */
 size_t lcb_sparsegpt_ws_bytes(int64_t n, int64_t k, int block);
 int lcb_sparsegpt_update(float* W, const float* U, double sparsity, int64_t n, int64_t k, int block, void* ws,
                          size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense contractions of the solvers (lazy-batch update ref: gptq/core.py:265, gptaq/core.py:272,319,
+ * sparsegpt/core.py:218; Cholesky trailing updates behind ref: gptq/core.py:213-224).
+ * lcb_set_gemm_mode selects how they are computed for every later call in this process and returns
+ * the previous mode:
+ *   1 (default)  tcgen05 tensor cores with the 3xTF32 split (x = hi + lo, three MMAs, fp32 TMEM
+ *                accumulator): ~2^-21 relative error per product instead of fp32's 2^-24
+ *   0            exact fp32 FFMA (SIMT) -- bit-reproduces the reference's fp32 results on the
+ *                golden cases; used by the parity tests as the anchor
+ * lcb_tgemm_nt exposes the tensor-core GEMM itself:  C[m,n] (+)= alpha * A[m,kd] * B[n,kd]^T, all
+ * row-major fp32 with leading dimensions in elements; kd % 4 == 0, ldc % 4 == 0, C 16 B aligned.
+ * kchain > 0 cuts the reduction into accumulation chains of kchain columns that are combined by fp32
+ * reduce-adds at L2 (the tensor core's own accumulator truncates; error grows with the chain length).
+ */
+int lcb_set_gemm_mode(int mode);
+size_t lcb_tgemm_ws_bytes(int64_t m, int64_t n, int64_t kd);
+int lcb_tgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m, int64_t n,
+                 int64_t kd, float alpha, int accumulate, int kchain, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (d) mask selection.  mask: uint8 [n, k], 1 = prune.

@@ -127,6 +127,7 @@ _OPTIONAL = [
     ("lcb_chol_inv_upper", [_vp, _vp, _i64, _vp, _f32, _vp, _sz, _vp, _vp], _i32),
     ("lcb_gptq_ws_bytes", [_i64, _i64, _i32], _sz),
     ("lcb_gptq_update", [_cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, _vp], _i32),
+    ("lcb_gptaq_p_ws_bytes", [_i64], _sz),
     ("lcb_gptaq_p", [_vp, _vp, _vp, _i64, _f32, _vp, _sz, _vp], _i32),
     ("lcb_sparsegpt_ws_bytes", [_i64, _i64, _i32], _sz),
     ("lcb_sparsegpt_update", [_vp, _vp, _f64, _i64, _i64, _i32, _vp, _sz, _vp], _i32),
@@ -135,6 +136,9 @@ _OPTIONAL = [
     ("lcb_mask_magnitude", [_vp, _i32, _vp, _i64, _i64, _f64, _vp, _sz, _vp], _i32),
     ("lcb_mask_ria", [_vp, _i32, _vp, _vp, _i64, _i64, _f64, _f32, _vp, _sz, _vp], _i32),
     ("lcb_apply_mask", [_vp, _i32, _vp, _i64, _vp], _i32),
+    ("lcb_set_gemm_mode", [_i32], _i32),
+    ("lcb_tgemm_ws_bytes", [_i64, _i64, _i64], _sz),
+    ("lcb_tgemm_nt", [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp, _sz, _vp], _i32),
 ]
 
 # every symbol include/lcb200.h declares (tests check that the library exports all of them)

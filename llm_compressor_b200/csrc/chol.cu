@@ -10,6 +10,8 @@
 //   2. right-looking blocked potrf, 128-wide panels: diagonal block factored (and inverted) by
 //      one CTA in shared memory, panel TRSM and trailing SYRK as fp32 GEMMs
 //   3. recursive blocked triangular inverse: batched GEMMs per level (log2(K/128) levels)
+#include <algorithm>
+
 #include "linalg.cuh"
 
 namespace lcb {
@@ -276,12 +278,20 @@ __global__ void put_diag_blocks_kernel(float* A, int64_t k, const float* dinv_al
 
 }  // namespace
 
+constexpr int SW = 512;        // super-panel width of the tensor-core path (Kd of the big SYRK)
+constexpr int TRI_TG_MIN = 1024;  // trtri levels with node size >= this run on the tensor cores
+constexpr int TG_CHAIN = 256;     // accumulation chain length (columns) of the tensor-core contractions
+
 static size_t chol_ws_floats(int64_t k) {
   const int64_t nblk = ceil_div(k, NB);
-  return (size_t)(k * k)            // work matrix
-         + (size_t)(k * k / 2 + k * NB)  // T of the trtri recursion
-         + (size_t)(nblk * NB * NB)  // inverted diagonal blocks
-         + (size_t)(k * NB)          // TRSM panel
+  const int64_t kp = ceil_div(k, 4) * 4;
+  const size_t t_exact = (size_t)(k * k / 2 + k * NB);
+  const size_t t_tg = (size_t)(9 * (kp / 2 + NB) * (kp / 2 + NB));  // planes of one trtri node
+  return (size_t)(k * k)                 // work matrix
+         + std::max(t_exact, t_tg)       // T of the trtri recursion / operand planes
+         + (size_t)(nblk * NB * NB)      // inverted diagonal blocks
+         + (size_t)(3 * kp * NB)         // TRSM panel + its hi / lo planes
+         + (size_t)(2 * kp * SW)         // hi / lo planes of a super-panel strip
          + 64;
 }
 
@@ -307,12 +317,18 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t nblk = ceil_div(k, NB);
+  const int64_t kp = ceil_div(k, 4) * 4;
   float* A = static_cast<float*>(ws);
   float* T = A + k * k;
-  float* dinv_all = T + (k * k / 2 + k * NB);
+  const size_t t_floats = std::max((size_t)(k * k / 2 + k * NB), (size_t)(9 * (kp / 2 + NB) * (kp / 2 + NB)));
+  float* dinv_all = T + t_floats;
   float* panel = dinv_all + nblk * NB * NB;
-  float* dsum = panel + k * NB;
-
+  float* panelH = panel + kp * NB;
+  float* panelL = panelH + kp * NB;
+  float* stripH = panelL + kp * NB;
+  float* stripL = stripH + kp * SW;
+  float* dsum = stripL + kp * SW;
+  const bool tg = gemm_mode() == 1 && k % 4 == 0 && tg_ok(ws, 4) && k > NB;
 
   diag_sum_kernel<<<1, 1024, 0, st>>>(H, k, dsum);
   LCB_LAUNCH_CHECK();
@@ -320,26 +336,64 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   gather_reverse_damp_kernel<<<g2, 256, 0, st>>>(A, H, perm, k, damp, dsum);
   LCB_LAUNCH_CHECK();
 
-  // ---- blocked right-looking Cholesky (lower) of A
-  for (int64_t b = 0; b < nblk; ++b) {
-    const int64_t j = b * NB;
-    const int nb = (int)std::min<int64_t>(NB, k - j);
-    float* Ajj = A + j * k + j;
-    float* dinv = dinv_all + b * NB * NB;
-    potf2_inv_kernel<<<1, 256, 0, st>>>(Ajj, k, nb, dinv, status);
-    LCB_LAUNCH_CHECK();
-    const int64_t m2 = k - j - nb;
-    if (m2 <= 0) break;
-    float* A21 = A + (j + nb) * k + j;
-    // L21 = A21 * L11^-T   (panel, ld NB)
-    int rc = sgemm(gemm_args(A21, k, dinv, NB, panel, NB, (int)m2, nb, nb, 1.0f, 0.0f, /*transB=*/1), st);
-    if (rc != LCB_OK) return rc;
-    LCB_CUDA(cudaMemcpy2DAsync(A21, (size_t)k * sizeof(float), panel, NB * sizeof(float), (size_t)nb * sizeof(float),
-                               (size_t)m2, cudaMemcpyDeviceToDevice, st));
-    // A22 -= L21 * L21^T   (lower tiles only)
-    rc = sgemm(gemm_args(panel, NB, panel, NB, A + (j + nb) * k + (j + nb), k, (int)m2, (int)m2, nb, -1.0f, 1.0f, 1,
-                         GEMM_LOWER_OUT), st);
-    if (rc != LCB_OK) return rc;
+  int rc;
+  if (!tg) {
+    // ---- blocked right-looking Cholesky (lower) of A, exact fp32
+    for (int64_t b = 0; b < nblk; ++b) {
+      const int64_t j = b * NB;
+      const int nb = (int)std::min<int64_t>(NB, k - j);
+      float* Ajj = A + j * k + j;
+      float* dinv = dinv_all + b * NB * NB;
+      potf2_inv_kernel<<<1, 256, 0, st>>>(Ajj, k, nb, dinv, status);
+      LCB_LAUNCH_CHECK();
+      const int64_t m2 = k - j - nb;
+      if (m2 <= 0) break;
+      float* A21 = A + (j + nb) * k + j;
+      // L21 = A21 * L11^-T   (panel, ld NB)
+      rc = sgemm(gemm_args(A21, k, dinv, NB, panel, NB, (int)m2, nb, nb, 1.0f, 0.0f, /*transB=*/1), st);
+      if (rc != LCB_OK) return rc;
+      LCB_CUDA(cudaMemcpy2DAsync(A21, (size_t)k * sizeof(float), panel, NB * sizeof(float), (size_t)nb * sizeof(float),
+                                 (size_t)m2, cudaMemcpyDeviceToDevice, st));
+      // A22 -= L21 * L21^T   (lower tiles only)
+      rc = sgemm(gemm_args(panel, NB, panel, NB, A + (j + nb) * k + (j + nb), k, (int)m2, (int)m2, nb, -1.0f, 1.0f, 1,
+                           GEMM_LOWER_OUT), st);
+      if (rc != LCB_OK) return rc;
+    }
+  } else {
+    // ---- tensor-core path: two-level right-looking Cholesky.  Inside a super-panel of SW columns the
+    // 128-wide panel updates touch only the rest of the super-panel strip (Kd = 128, small N); the
+    // trailing matrix beyond the strip gets one SYRK with Kd = SW per super-panel.
+    for (int64_t j0 = 0; j0 < k; j0 += SW) {
+      const int64_t j1 = std::min<int64_t>(j0 + SW, k);
+      for (int64_t j = j0; j < j1; j += NB) {
+        const int nb = (int)std::min<int64_t>(NB, k - j);
+        float* Ajj = A + j * k + j;
+        float* dinv = dinv_all + (j / NB) * NB * NB;
+        potf2_inv_kernel<<<1, 256, 0, st>>>(Ajj, k, nb, dinv, status);
+        LCB_LAUNCH_CHECK();
+        const int64_t m2 = k - j - nb;
+        if (m2 <= 0) break;
+        float* A21 = A + (j + nb) * k + j;
+        // L21 = A21 * L11^-T in place (a CTA reads its 128 rows completely before it writes them)
+        rc = sgemm(gemm_args(A21, k, dinv, NB, A21, k, (int)m2, nb, nb, 1.0f, 0.0f, /*transB=*/1), st);
+        if (rc != LCB_OK) return rc;
+        const int64_t nrest = j1 - (j + nb);  // columns of the strip still to be updated
+        if (nrest > 0) {
+          if ((rc = split_tf32(A21, k, (int)m2, nb, panelH, panelL, NB, 0, st)) != LCB_OK) return rc;
+          rc = tgemm_nt(panelH, panelL, NB, panelH, panelL, NB, A + (j + nb) * k + (j + nb), k, (int)m2, (int)nrest, nb,
+                        -1.0f, TG_LOWER_OUT, st);
+          if (rc != LCB_OK) return rc;
+        }
+      }
+      const int64_t m3 = k - j1;
+      if (m3 > 0) {
+        const int kd = (int)(j1 - j0);
+        if ((rc = split_tf32(A + j1 * k + j0, k, (int)m3, kd, stripH, stripL, SW, 0, st)) != LCB_OK) return rc;
+        rc = tgemm_nt(stripH, stripL, SW, stripH, stripL, SW, A + j1 * k + j1, k, (int)m3, (int)m3, kd, -1.0f,
+                      TG_LOWER_OUT, st, TG_CHAIN);
+        if (rc != LCB_OK) return rc;
+      }
+    }
   }
   zero_strict_upper_kernel<<<g2, 256, 0, st>>>(A, k);
   LCB_LAUNCH_CHECK();
@@ -349,6 +403,35 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   // ---- recursive triangular inverse, in place: [[A,0],[C,B]]^-1 = [[A^-1,0],[-B^-1 C A^-1, B^-1]]
   for (int64_t s = NB; s < k; s *= 2) {
     const int64_t nodes = ceil_div(k, 2 * s);
+    if (tg && s >= TRI_TG_MIN) {
+      // tensor cores, node by node:  T^T = A^-T C^T  and  C <- -B^-1 T  as two NT GEMMs on hi/lo planes
+      for (int64_t t0 = 0; t0 < nodes; ++t0) {
+        const int64_t base = t0 * 2 * s;
+        const int64_t sB = std::min<int64_t>(s, k - base - s);
+        if (sB <= 0) break;
+        float* Ainv = A + base * k + base;
+        float* Cblk = A + (base + s) * k + base;
+        float* Binv = A + (base + s) * k + (base + s);
+        float* ATh = T;                 // [s, s]   planes of Ainv^T (upper triangular)
+        float* ATl = ATh + s * s;
+        float* Ch = ATl + s * s;        // [sB, s]  planes of C
+        float* Cl = Ch + sB * s;
+        float* TT = Cl + sB * s;        // [s, sB]  T^T
+        float* TTh = TT + s * sB;
+        float* TTl = TTh + s * sB;
+        float* Bh = TTl + s * sB;       // [sB, sB] planes of Binv (lower triangular)
+        float* Bl = Bh + sB * sB;
+        if ((rc = split_tf32(Ainv, k, (int)s, (int)s, ATh, ATl, s, 1, st)) != LCB_OK) return rc;
+        if ((rc = split_tf32(Cblk, k, (int)sB, (int)s, Ch, Cl, s, 0, st)) != LCB_OK) return rc;
+        if ((rc = split_tf32(Binv, k, (int)sB, (int)sB, Bh, Bl, sB, 0, st)) != LCB_OK) return rc;
+        rc = tgemm_nt(ATh, ATl, s, Ch, Cl, s, TT, sB, (int)s, (int)sB, (int)s, 1.0f, TG_STORE | TG_A_UPPER, st, TG_CHAIN);
+        if (rc != LCB_OK) return rc;
+        if ((rc = split_tf32(TT, sB, (int)s, (int)sB, TTh, TTl, sB, 0, st)) != LCB_OK) return rc;
+        rc = tgemm_nt(Bh, Bl, sB, TTh, TTl, sB, Cblk, k, (int)sB, (int)s, (int)sB, -1.0f, TG_STORE | TG_A_LOWER, st, TG_CHAIN);
+        if (rc != LCB_OK) return rc;
+      }
+      continue;
+    }
     for (int64_t t0 = 0; t0 < nodes;) {
       // batch consecutive nodes with the same (full) size; the ragged last node goes alone
       const int64_t base = t0 * 2 * s;
@@ -363,7 +446,7 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
       float* Binv = A + (base + s) * k + (base + s);
       GemmArgs g1 = gemm_args(Cblk, k, Ainv, k, T, s, (int)sB0, (int)s, (int)s, 1.0f, 0.0f, 0, GEMM_B_LOWER);
       g1.batch = (int)cnt; g1.strideA = g1.strideB = 2 * s * (k + 1); g1.strideC = s * s;
-      int rc = sgemm(g1, st);
+      rc = sgemm(g1, st);
       if (rc != LCB_OK) return rc;
       GemmArgs g2a = gemm_args(Binv, k, T, s, Cblk, k, (int)sB0, (int)s, (int)sB0, -1.0f, 0.0f, 0, GEMM_A_LOWER);
       g2a.batch = (int)cnt; g2a.strideA = g2a.strideC = 2 * s * (k + 1); g2a.strideB = s * s;

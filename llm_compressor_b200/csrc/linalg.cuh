@@ -40,4 +40,26 @@ inline GemmArgs gemm_args(const float* A, int64_t lda, const float* B, int64_t l
   return g;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32-accurate tensor-core GEMM (tgemm.cu): C[M,N] (+)= alpha * A[M,Kd] * B[N,Kd]^T on tcgen05 with
+// the 3xTF32 split.  Operands are given as pre-split hi / lo planes (split_tf32), K-major.
+//   TG_STORE      C = alpha*A*B^T (default: C += alpha*A*B^T, reduce-add at L2)
+//   TG_LOWER_OUT  only tiles of C touching the lower triangle are produced
+//   TG_A_LOWER    A[m][k] == 0 for k > m  (k-loop cut per row tile)
+//   TG_A_UPPER    A[m][k] == 0 for k < m
+// Requirements: all bases 16 B aligned, leading dimensions multiples of 4.
+enum { TG_STORE = 1, TG_LOWER_OUT = 2, TG_A_LOWER = 4, TG_A_UPPER = 8 };
+// kchain > 0: the reduction is cut into accumulation chains of at most kchain columns, each reduce-added
+// into C separately.  The tensor core's fp32 accumulator truncates, so the error of one chain grows
+// linearly with its length (3 * kchain / 8 MMAs); 0 = one chain per tile.
+int tgemm_nt(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, float* C,
+             int64_t ldc, int M, int N, int Kd, float alpha, int flags, cudaStream_t st, int kchain = 0);
+// hi = tf32(x), lo = x - hi; transpose != 0: out[c][r] = split(in[r][c])
+int split_tf32(const float* in, int64_t ld_in, int rows, int cols, float* hi, float* lo, int64_t ld_out, int transpose,
+               cudaStream_t st);
+inline bool tg_ok(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0; }
+
+// solver GEMM precision: 0 = exact fp32 FFMA (sgemm), 1 = 3xTF32 on tcgen05 (default)
+int gemm_mode();
+
 }  // namespace lcb

@@ -20,7 +20,15 @@ constexpr int TPR = BLK / CPT;     // threads per row = 8
 constexpr int ROWS_PER_CTA = 32;   // 256 threads
 constexpr int ULD = BLK + 4;
 
+constexpr int SUPER = 1024;        // second-level lazy batch of the tensor-core path (columns)
+
 enum { MODE_QUANT = 0, MODE_SPARSE = 1 };
+
+__device__ __forceinline__ float tf32_hi(float v) {
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  return __uint_as_float(hb);
+}
 
 struct BlockArgs {
   float* W;           // [n, k] working weight (block columns are read; SPARSE: written back)
@@ -31,8 +39,11 @@ struct BlockArgs {
   const float* zeros;
   const uint8_t* keep;   // [n, k] or null
   const uint8_t* prune;  // [n, BLK] (SPARSE) mask for this block
-  float* Err;         // [n, BLK]
-  float* W1out;       // [n, BLK] (GPTAQ) block after in-block updates, or null
+  float* Err;         // [n, ldE] error columns of this block at column offset eoff (hi plane when ErrLo != null)
+  float* ErrLo;       // tf32 split: lo plane (Err = hi + lo), or null for one exact fp32 plane
+  float* W1out;       // (GPTAQ) block after in-block updates, same geometry as Err, or null
+  float* W1Lo;
+  int64_t ldE, eoff;
   int64_t n, k;
   int64_t i1;         // first column of the block
   int count;          // columns in the block (<= BLK)
@@ -47,12 +58,21 @@ __global__ void __launch_bounds__(256) block_step_kernel(BlockArgs a) {
   float* Us = smem;                               // [BLK][ULD]
   float* Ps = HAS_P ? smem + BLK * ULD : nullptr;  // [BLK][ULD]
   const int t = threadIdx.x;
-  // stage the diagonal blocks (zero filled beyond `count`)
-  for (int e = t; e < BLK * BLK; e += 256) {
-    const int r = e / BLK, c = e % BLK;
-    const bool in = r < a.count && c < a.count;
-    Us[r * ULD + c] = in ? a.U[(a.i1 + r) * a.k + a.i1 + c] : 0.0f;
-    if (HAS_P) Ps[r * ULD + c] = in ? a.P[(a.i1 + r) * a.k + a.i1 + c] : 0.0f;
+  const bool grouped = (MODE == MODE_QUANT) && a.group > 0;
+  const int gs = grouped ? (int)a.group : 1;
+  // With one group spanning the whole block and no P nothing downstream reads the in-block
+  // propagation, so only diag(U) is needed.
+  const bool need_prop = HAS_P || !grouped || gs < a.count;
+  if (need_prop) {
+    // stage the diagonal blocks (zero filled beyond `count`)
+    for (int e = t; e < BLK * BLK; e += 256) {
+      const int r = e / BLK, c = e % BLK;
+      const bool in = r < a.count && c < a.count;
+      Us[r * ULD + c] = in ? a.U[(a.i1 + r) * a.k + a.i1 + c] : 0.0f;
+      if (HAS_P) Ps[r * ULD + c] = in ? a.P[(a.i1 + r) * a.k + a.i1 + c] : 0.0f;
+    }
+  } else if (t < BLK) {
+    Us[t * ULD + t] = t < a.count ? a.U[(a.i1 + t) * a.k + a.i1 + t] : 0.0f;
   }
   __syncthreads();
 
@@ -81,14 +101,11 @@ __global__ void __launch_bounds__(256) block_step_kernel(BlockArgs a) {
     for (int j = 0; j < CPT; ++j)
       if (c0 + j < a.count && a.prune[rr * BLK + c0 + j]) prunebits |= 1u << j;
   }
-  const bool grouped = (MODE == MODE_QUANT) && a.group > 0;
-  const int gs = grouped ? (int)a.group : 1;
   float s_cur = 1.0f, z_cur = 0.0f;
   if (MODE == MODE_QUANT && !grouped) {  // per-row parameters
     s_cur = a.scales[rr * a.G];
     z_cur = a.zeros[rr * a.G];
   }
-  const bool need_prop = HAS_P || !grouped || gs < a.count;
   const int lane = t & 31;
   const int lane_row_base = lane - t8;  // lane of t8 == 0 for this row
 
@@ -122,7 +139,6 @@ __global__ void __launch_bounds__(256) block_step_kernel(BlockArgs a) {
       const float e = __fdiv_rn(__fsub_rn(wi, q), d);
       if (t8 == ib) { qv[ii] = q; ev[ii] = e; }
       // propagate to columns j >= i of the block: w_j -= e * U[i][j] (- w_i * P[i][j]).
-      // With one group spanning the whole block and no P nothing downstream reads the result.
       if (need_prop && i < a.count && t8 >= ib) {
         const float* urow = Us + i * ULD + c0;
         const float* prow = HAS_P ? Ps + i * ULD + c0 : nullptr;
@@ -145,8 +161,72 @@ __global__ void __launch_bounds__(256) block_step_kernel(BlockArgs a) {
       if (MODE == MODE_QUANT) a.Q[rr * a.k + a.i1 + c0 + j] = qv[j];
       else a.W[rr * a.k + a.i1 + c0 + j] = qv[j];
     }
-    a.Err[rr * BLK + c0 + j] = (c0 + j < a.count) ? ev[j] : 0.0f;
-    if (a.W1out) a.W1out[rr * BLK + c0 + j] = (c0 + j < a.count) ? w[j] : 0.0f;
+    const int64_t eo = rr * a.ldE + a.eoff + c0 + j;
+    const float e = (c0 + j < a.count) ? ev[j] : 0.0f;
+    if (a.ErrLo) {
+      const float h = tf32_hi(e);
+      a.Err[eo] = h;
+      a.ErrLo[eo] = __fsub_rn(e, h);
+    } else {
+      a.Err[eo] = e;
+    }
+    if (a.W1out) {
+      const float w1 = (c0 + j < a.count) ? w[j] : 0.0f;
+      if (a.W1Lo) {
+        const float h = tf32_hi(w1);
+        a.W1out[eo] = h;
+        a.W1Lo[eo] = __fsub_rn(w1, h);
+      } else {
+        a.W1out[eo] = w1;
+      }
+    }
+  }
+}
+
+// Grouped quantiser whose group spans the whole block (int4-g[128], the headline configuration), no P:
+// nothing inside the block depends on the in-block propagation (ref: gptq/core.py:249-262 with
+// group_size == block_size), so the block step is elementwise: q = QDQ(w) * MASK, e = (w - q) / diag(U).
+__global__ void __launch_bounds__(256) block_quant_kernel(BlockArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of the [n, BLK] block
+  const int64_t row = idx / (BLK / 4);
+  const int c0 = (int)(idx % (BLK / 4)) * 4;
+  if (row >= a.n) return;
+  const int64_t g = a.i1 / a.group;
+  const float s = a.scales[row * a.G + g], z = a.zeros[row * a.G + g];
+  float w[4] = {0.f, 0.f, 0.f, 0.f}, q[4], e[4];
+  const int64_t wo = row * a.k + a.i1 + c0;
+  if (c0 + 3 < a.count) {
+    const float4 v = *reinterpret_cast<const float4*>(a.W + wo);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (c0 + j < a.count) w[j] = a.W[wo + j];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool in = c0 + j < a.count;
+    float code;
+    float qq = fake_quant<LCB_F32>(a.c, w[j], s, z, code);
+    if (a.keep && in && !a.keep[wo + j]) qq = 0.0f;  // q *= MASK (ref :258)
+    const float d = in ? a.U[(a.i1 + c0 + j) * (a.k + 1)] : 1.0f;
+    q[j] = qq;
+    e[j] = in ? __fdiv_rn(__fsub_rn(w[j], qq), d) : 0.0f;
+  }
+  if (c0 + 3 < a.count) {
+    *reinterpret_cast<float4*>(a.Q + wo) = make_float4(q[0], q[1], q[2], q[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (c0 + j < a.count) a.Q[wo + j] = q[j];
+  }
+  const int64_t eo = row * a.ldE + a.eoff + c0;
+  if (a.ErrLo) {
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = tf32_hi(e[j]); l[j] = __fsub_rn(e[j], h[j]); }
+    *reinterpret_cast<float4*>(a.Err + eo) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(a.ErrLo + eo) = make_float4(l[0], l[1], l[2], l[3]);
+  } else {
+    *reinterpret_cast<float4*>(a.Err + eo) = make_float4(e[0], e[1], e[2], e[3]);
   }
 }
 
@@ -180,12 +260,115 @@ size_t select_ws_bytes();
 
 using namespace lcb;
 
-static size_t gptq_ws_floats(int64_t n, int block) { return (size_t)(2 * n * block + 64); }
+// Trailing updates on the tensor-core path use a two-level lazy batch: after each 128-column block
+// only the rest of the current SUPER-column super-block is updated (Kd = 128); the columns beyond it
+// receive one GEMM with Kd = SUPER per super-block, which cuts the read-modify-write traffic on W by
+// SUPER / 128 relative to the reference's schedule (same sums, different fp32 association).
+static bool use_tg(const float* W, const float* U, const float* P, int64_t k) {
+  return gemm_mode() == 1 && tg_ok(W, k) && tg_ok(U, k) && (P == nullptr || tg_ok(P, k));
+}
+static int64_t super_cols(int64_t k) { return std::min<int64_t>(SUPER, ceil_div(k, BLK) * BLK); }
+
+static size_t gptq_ws_floats(int64_t n, int64_t k, int block) {
+  const size_t exact = (size_t)(2 * n * block);
+  const size_t tg = (size_t)(4 * n * super_cols(k)) + (size_t)(4 * k * k);
+  return std::max(exact, tg) + 64;
+}
 
 extern "C" size_t lcb_gptq_ws_bytes(int64_t n, int64_t k, int block) {
-  (void)k;
-  return gptq_ws_floats(n, block) * sizeof(float);
+  return gptq_ws_floats(n, k, block) * sizeof(float);
 }
+
+namespace lcb {
+// Shared block loop of GPTQ / GPTAQ (MODE_QUANT) and SparseGPT (MODE_SPARSE).  `pre_block(i1, count)`
+// runs before each block step (SparseGPT: saliency + threshold + mask).
+template <typename PreBlock>
+static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const float* P, int64_t n, int64_t k,
+                          float* wsf, cudaStream_t st, PreBlock pre_block) {
+  const bool tg = use_tg(W, U, P, k);
+  const int smem = (P ? 2 : 1) * BLK * ULD * (int)sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(n, ROWS_PER_CTA);
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(a.Q)) & 15) == 0 && k % 4 == 0;
+  auto step = [&]() -> int {
+    if (mode == MODE_QUANT && !P && a.group >= a.count && a.group > 0 && aligned16) {
+      block_quant_kernel<<<(unsigned)ceil_div(n * (BLK / 4), 256), 256, 0, st>>>(a);
+      LCB_LAUNCH_CHECK();
+      return LCB_OK;
+    }
+    if (mode == MODE_SPARSE) block_step_kernel<MODE_SPARSE, false><<<grid, 256, smem, st>>>(a);
+    else if (P) block_step_kernel<MODE_QUANT, true><<<grid, 256, smem, st>>>(a);
+    else block_step_kernel<MODE_QUANT, false><<<grid, 256, smem, st>>>(a);
+    LCB_LAUNCH_CHECK();
+    return LCB_OK;
+  };
+  int rc;
+  if (!tg) {
+    a.Err = wsf; a.ErrLo = nullptr; a.ldE = BLK; a.eoff = 0;
+    a.W1out = P ? wsf + n * BLK : nullptr; a.W1Lo = nullptr;
+    for (int64_t i1 = 0; i1 < k; i1 += BLK) {
+      const int64_t i2 = std::min<int64_t>(i1 + BLK, k);
+      a.i1 = i1; a.count = (int)(i2 - i1);
+      if ((rc = pre_block(i1, a.count)) != LCB_OK) return rc;
+      if ((rc = step()) != LCB_OK) return rc;
+      if (i2 < k) {
+        // W[:, i2:] -= Err1 @ U[i1:i2, i2:]  (- W1 @ P[i1:i2, i2:])      ref gptq :265, gptaq :319
+        rc = sgemm(gemm_args(a.Err, BLK, U + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), a.count, -1.0f, 1.0f, 0), st);
+        if (rc != LCB_OK) return rc;
+        if (P) {
+          rc = sgemm(gemm_args(a.W1out, BLK, P + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), a.count, 1.0f, 1.0f, 0), st);
+          if (rc != LCB_OK) return rc;
+        }
+      }
+    }
+    return LCB_OK;
+  }
+  // ---- tensor-core path
+  const int64_t S = super_cols(k);
+  float* ErrH = wsf;
+  float* ErrL = ErrH + n * S;
+  float* W1H = ErrL + n * S;
+  float* W1L = W1H + n * S;
+  float* UTh = W1L + n * S;
+  float* UTl = UTh + k * k;
+  float* PTh = UTl + k * k;
+  float* PTl = PTh + k * k;
+  if ((rc = split_tf32(U, k, (int)k, (int)k, UTh, UTl, k, /*transpose=*/1, st)) != LCB_OK) return rc;
+  if (P && (rc = split_tf32(P, k, (int)k, (int)k, PTh, PTl, k, 1, st)) != LCB_OK) return rc;
+  a.Err = ErrH; a.ErrLo = ErrL; a.ldE = S;
+  a.W1out = P ? W1H : nullptr; a.W1Lo = P ? W1L : nullptr;
+  for (int64_t s0 = 0; s0 < k; s0 += S) {
+    const int64_t s1 = std::min<int64_t>(s0 + S, k);
+    for (int64_t i1 = s0; i1 < s1; i1 += BLK) {
+      const int64_t i2 = std::min<int64_t>(i1 + BLK, k);
+      a.i1 = i1; a.count = (int)(i2 - i1); a.eoff = i1 - s0;
+      if ((rc = pre_block(i1, a.count)) != LCB_OK) return rc;
+      if ((rc = step()) != LCB_OK) return rc;
+      if (i2 < s1) {  // rest of the super-block, Kd = 128 (short last block: its zero padded columns add 0)
+        const int kd = (int)std::min<int64_t>(BLK, S - a.eoff);
+        rc = tgemm_nt(ErrH + a.eoff, ErrL + a.eoff, S, UTh + i2 * k + i1, UTl + i2 * k + i1, k, W + i2, k, (int)n,
+                      (int)(s1 - i2), kd, -1.0f, 0, st);
+        if (rc != LCB_OK) return rc;
+        if (P) {
+          rc = tgemm_nt(W1H + a.eoff, W1L + a.eoff, S, PTh + i2 * k + i1, PTl + i2 * k + i1, k, W + i2, k, (int)n,
+                        (int)(s1 - i2), kd, 1.0f, 0, st);
+          if (rc != LCB_OK) return rc;
+        }
+      }
+    }
+    if (s1 < k) {  // everything beyond the super-block, Kd = S
+      rc = tgemm_nt(ErrH, ErrL, S, UTh + s1 * k + s0, UTl + s1 * k + s0, k, W + s1, k, (int)n, (int)(k - s1),
+                    (int)(s1 - s0), -1.0f, 0, st);
+      if (rc != LCB_OK) return rc;
+      if (P) {
+        rc = tgemm_nt(W1H, W1L, S, PTh + s1 * k + s0, PTl + s1 * k + s0, k, W + s1, k, (int)n, (int)(k - s1),
+                      (int)(s1 - s0), 1.0f, 0, st);
+        if (rc != LCB_OK) return rc;
+      }
+    }
+  }
+  return LCB_OK;
+}
+}  // namespace lcb
 
 extern "C" int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, const float* U, const float* P,
                                const float* scales, const float* zeros, const uint8_t* keep, int64_t n, int64_t k,
@@ -197,15 +380,13 @@ extern "C" int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, con
     LCB_REQUIRE(BLK % group == 0 && group % CPT == 0 && k % group == 0,
                 "lcb_gptq_update: group must divide 128, be a multiple of 16 and divide k (got %lld)", (long long)group);
   }
-  if (ws == nullptr || ws_bytes < lcb_gptq_ws_bytes(n, k, block)) {
-    set_error("lcb_gptq_update: workspace of %zu bytes needed", lcb_gptq_ws_bytes(n, k, block));
+  if (ws == nullptr || ws_bytes < lcb_gptq_ws_bytes(n, k, block) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("lcb_gptq_update: 16-byte aligned workspace of %zu bytes needed", lcb_gptq_ws_bytes(n, k, block));
     return LCB_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BlockArgs a{};
   a.W = W; a.Q = Q; a.U = U; a.P = P; a.scales = scales; a.zeros = zeros; a.keep = keep;
-  a.Err = static_cast<float*>(ws);
-  a.W1out = P ? a.Err + n * BLK : nullptr;
   a.n = n; a.k = k; a.group = group; a.G = group > 0 ? k / group : 1;
   a.c.qtype = cfg->qtype; a.c.zero_point = cfg->zero_point ? 1 : 0;
   a.c.scale_emax = (float)((1 << ((cfg->scale_ebits > 0 ? cfg->scale_ebits : 8) - 1)) - 1);
@@ -213,24 +394,7 @@ extern "C" int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, con
   const int smem = (P ? 2 : 1) * BLK * ULD * (int)sizeof(float);
   LCB_CUDA(cudaFuncSetAttribute(block_step_kernel<MODE_QUANT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   LCB_CUDA(cudaFuncSetAttribute(block_step_kernel<MODE_QUANT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const unsigned grid = (unsigned)ceil_div(n, ROWS_PER_CTA);
-  for (int64_t i1 = 0; i1 < k; i1 += BLK) {
-    const int64_t i2 = std::min<int64_t>(i1 + BLK, k);
-    a.i1 = i1; a.count = (int)(i2 - i1);
-    if (P) block_step_kernel<MODE_QUANT, true><<<grid, 256, smem, st>>>(a);
-    else block_step_kernel<MODE_QUANT, false><<<grid, 256, smem, st>>>(a);
-    LCB_LAUNCH_CHECK();
-    if (i2 < k) {
-      // W[:, i2:] -= Err1 @ U[i1:i2, i2:]  (- W1 @ P[i1:i2, i2:])      ref gptq :265, gptaq :319
-      int rc = sgemm(gemm_args(a.Err, BLK, U + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), a.count, -1.0f, 1.0f, 0), st);
-      if (rc != LCB_OK) return rc;
-      if (P) {
-        rc = sgemm(gemm_args(a.W1out, BLK, P + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), a.count, 1.0f, 1.0f, 0), st);
-        if (rc != LCB_OK) return rc;
-      }
-    }
-  }
-  return LCB_OK;
+  return run_block_loop(a, MODE_QUANT, W, U, P, n, k, static_cast<float*>(ws), st, [](int64_t, int) { return LCB_OK; });
 }
 
 // P = alpha * triu(dXXT @ U^T, 1) @ U   (ref: gptaq/core.py:272)
@@ -242,51 +406,74 @@ __global__ void triu1_scale_kernel(float* A, int64_t k, float alpha) {
 }
 }  // namespace lcb
 
+extern "C" size_t lcb_gptaq_p_ws_bytes(int64_t k) { return (size_t)(7 * k * k + 64) * sizeof(float); }
+
 extern "C" int lcb_gptaq_p(float* P, float* dxxt, const float* U, int64_t k, float alpha, void* ws, size_t ws_bytes,
                            void* stream) {
   LCB_REQUIRE(P && dxxt && U && k > 0, "lcb_gptaq_p: bad arguments");
-  if (ws == nullptr || ws_bytes < (size_t)(k * k) * sizeof(float)) {
-    set_error("lcb_gptaq_p: workspace of %zu bytes needed", (size_t)(k * k) * sizeof(float));
+  const bool tg = gemm_mode() == 1 && tg_ok(P, k) && tg_ok(ws, 4);
+  const size_t need = tg ? lcb_gptaq_p_ws_bytes(k) : (size_t)(k * k) * sizeof(float);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("lcb_gptaq_p: workspace of %zu bytes needed", need);
     return LCB_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* T = static_cast<float*>(ws);
-  int rc = sgemm(gemm_args(dxxt, k, U, k, T, k, (int)k, (int)k, (int)k, 1.0f, 0.0f, /*transB=*/1), st);
-  if (rc != LCB_OK) return rc;
   dim3 g2((unsigned)ceil_div(k, 256), (unsigned)k);
+  int rc;
+  if (!tg) {
+    rc = sgemm(gemm_args(dxxt, k, U, k, T, k, (int)k, (int)k, (int)k, 1.0f, 0.0f, /*transB=*/1), st);
+    if (rc != LCB_OK) return rc;
+    triu1_scale_kernel<<<g2, 256, 0, st>>>(T, k, alpha);
+    LCB_LAUNCH_CHECK();
+    return sgemm(gemm_args(T, k, U, k, P, k, (int)k, (int)k, (int)k, 1.0f, 0.0f, 0), st);
+  }
+  float* Ah = T + k * k;   // planes of dXXT, later of triu(T, 1)
+  float* Al = Ah + k * k;
+  float* Uh = Al + k * k;  // planes of U
+  float* Ul = Uh + k * k;
+  float* UTh = Ul + k * k;  // planes of U^T
+  float* UTl = UTh + k * k;
+  if ((rc = split_tf32(dxxt, k, (int)k, (int)k, Ah, Al, k, 0, st)) != LCB_OK) return rc;
+  if ((rc = split_tf32(U, k, (int)k, (int)k, Uh, Ul, k, 0, st)) != LCB_OK) return rc;
+  if ((rc = split_tf32(U, k, (int)k, (int)k, UTh, UTl, k, 1, st)) != LCB_OK) return rc;
+  // T = dXXT @ U^T
+  rc = tgemm_nt(Ah, Al, k, Uh, Ul, k, T, k, (int)k, (int)k, (int)k, 1.0f, TG_STORE, st);
+  if (rc != LCB_OK) return rc;
   triu1_scale_kernel<<<g2, 256, 0, st>>>(T, k, alpha);
   LCB_LAUNCH_CHECK();
-  return sgemm(gemm_args(T, k, U, k, P, k, (int)k, (int)k, (int)k, 1.0f, 0.0f, 0), st);
+  if ((rc = split_tf32(T, k, (int)k, (int)k, Ah, Al, k, 0, st)) != LCB_OK) return rc;
+  // P = triu(T, 1) @ U = T' @ (U^T)^T; T' is strictly upper triangular: the k-loop starts at the row tile
+  return tgemm_nt(Ah, Al, k, UTh, UTl, k, P, k, (int)k, (int)k, (int)k, 1.0f, TG_STORE | TG_A_UPPER, st);
 }
 
+static size_t sparse_tail_bytes(int64_t n) { return (size_t)(n * BLK) * (sizeof(float) + 1) + 512 + select_ws_bytes(); }
+
 extern "C" size_t lcb_sparsegpt_ws_bytes(int64_t n, int64_t k, int block) {
-  (void)k;
-  return (size_t)(n * block) * (2 * sizeof(float) + 1) + 256 + select_ws_bytes();
+  return gptq_ws_floats(n, k, block) * sizeof(float) + sparse_tail_bytes(n);
 }
 
 extern "C" int lcb_sparsegpt_update(float* W, const float* U, double sparsity, int64_t n, int64_t k, int block,
                                     void* ws, size_t ws_bytes, void* stream) {
   LCB_REQUIRE(W && U && n > 0 && k > 0, "lcb_sparsegpt_update: bad arguments");
   LCB_REQUIRE(block == BLK, "lcb_sparsegpt_update: block must be 128");
-  if (ws == nullptr || ws_bytes < lcb_sparsegpt_ws_bytes(n, k, block)) {
-    set_error("lcb_sparsegpt_update: workspace of %zu bytes needed", lcb_sparsegpt_ws_bytes(n, k, block));
+  if (ws == nullptr || ws_bytes < lcb_sparsegpt_ws_bytes(n, k, block) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("lcb_sparsegpt_update: 16-byte aligned workspace of %zu bytes needed", lcb_sparsegpt_ws_bytes(n, k, block));
     return LCB_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* Err = static_cast<float*>(ws);
-  float* metric = Err + n * BLK;
+  float* wsf = static_cast<float*>(ws);
+  float* metric = wsf + gptq_ws_floats(n, k, block);
   float* thresh = metric + n * BLK;                                 // 64 floats reserved
   uint8_t* prune = reinterpret_cast<uint8_t*>(thresh + 64);          // [n, BLK]
   void* sel_ws = prune + ((n * BLK + 255) / 256) * 256;
   BlockArgs a{};
-  a.W = W; a.U = U; a.Err = Err; a.prune = prune; a.n = n; a.k = k; a.group = 0; a.G = 1;
+  a.W = W; a.U = U; a.prune = prune; a.n = n; a.k = k; a.group = 0; a.G = 1;
   a.c.f = make_fmt(LCB_E_INT8);
   const int smem = BLK * ULD * (int)sizeof(float);
   LCB_CUDA(cudaFuncSetAttribute(block_step_kernel<MODE_SPARSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const unsigned grid = (unsigned)ceil_div(n, ROWS_PER_CTA);
-  for (int64_t i1 = 0; i1 < k; i1 += BLK) {
-    const int64_t i2 = std::min<int64_t>(i1 + BLK, k);
-    const int count = (int)(i2 - i1);
+  auto pre = [&](int64_t i1, int count) -> int {
+    // mask of the block from its state at block entry (ref: sparsegpt/core.py:201-203)
     const int64_t numel = n * count;
     sparse_metric_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, st>>>(W, U, metric, n, k, i1, count);
     LCB_LAUNCH_CHECK();
@@ -296,13 +483,7 @@ extern "C" int lcb_sparsegpt_update(float* W, const float* U, double sparsity, i
     if (rc != LCB_OK) return rc;
     sparse_mask_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, st>>>(metric, thresh, prune, n, count);
     LCB_LAUNCH_CHECK();
-    a.i1 = i1; a.count = count;
-    block_step_kernel<MODE_SPARSE, false><<<grid, 256, smem, st>>>(a);
-    LCB_LAUNCH_CHECK();
-    if (i2 < k) {
-      rc = sgemm(gemm_args(Err, BLK, U + i1 * k + i2, k, W + i2, k, (int)n, (int)(k - i2), count, -1.0f, 1.0f, 0), st);
-      if (rc != LCB_OK) return rc;
-    }
-  }
-  return LCB_OK;
+    return LCB_OK;
+  };
+  return run_block_loop(a, MODE_SPARSE, W, U, nullptr, n, k, wsf, st, pre);
 }

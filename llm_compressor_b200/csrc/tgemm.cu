@@ -11,6 +11,10 @@
 // K-major fp32 tiles per stage through TMA (128B swizzle), issues 12 tcgen05.mma.kind::tf32
 // (M=128, N=256, K=8) per 32-wide k block, and reduce-adds the accumulator into C with TMA
 // (cp.reduce.async.bulk.tensor .add.f32 at L2) -- C is never read by the SMs.
+#include <algorithm>
+#include <atomic>
+
+#include "linalg.cuh"
 #include "umma.cuh"
 
 namespace lcb {
@@ -60,7 +64,9 @@ struct TgArgs {
   int M, N, Kd;
   float alpha;
   int tiles_m, tiles_n;
-  int lower_only;  // skip tiles entirely above the diagonal (SYRK on a lower-triangular target)
+  int flags;  // TG_* (linalg.cuh)
+  int kcb;    // k blocks per accumulation chain (work unit = tile x chain)
+  int nchunks;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -80,6 +86,23 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = a.tiles_m * a.tiles_n;
   const int kblocks = (a.Kd + BK - 1) / BK;
+  const bool lower_only = (a.flags & TG_LOWER_OUT) != 0;
+  // Work unit u = (tile, accumulation chain): the tile's k range (cut when A is triangular: the zero
+  // part is never loaded) is processed in chains of at most kcb k-blocks, each reduce-added into C on
+  // its own, which bounds the length of the truncating fp32 accumulation inside the tensor core.
+  const int nunits = num_tiles * a.nchunks;
+  auto unit = [&](int u, int& m0, int& n0, int& kb0, int& kb1) -> bool {
+    const int tile = u % num_tiles, ch = u / num_tiles;
+    m0 = (tile / a.tiles_n) * BM;
+    n0 = (tile % a.tiles_n) * BN;
+    if (lower_only && n0 > m0 + BM - 1) return false;
+    int lo = 0, hi = kblocks;
+    if (a.flags & TG_A_LOWER) hi = min(kblocks, (m0 + BM + BK - 1) / BK);
+    if (a.flags & TG_A_UPPER) lo = min(m0 / BK, kblocks - 1);
+    kb0 = max(lo, ch * a.kcb);
+    kb1 = min(hi, (ch + 1) * a.kcb);
+    return kb1 > kb0;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ah)) : "memory");
@@ -101,16 +124,14 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *tmem_slot;
 
-  auto skip_tile = [&](int m0, int n0) { return a.lower_only && n0 > m0 + BM - 1; };
-
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
-        if (skip_tile(m0, n0)) continue;
-        for (int kb = 0; kb < kblocks; ++kb) {
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        int m0, n0, kb0, kb1;
+        if (!unit(u, m0, n0, kb0, kb1)) continue;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
@@ -128,15 +149,15 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
-        if (skip_tile(m0, n0)) continue;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        int m0, n0, kb0, kb1;
+        if (!unit(u, m0, n0, kb0, kb1)) continue;
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
@@ -146,12 +167,12 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
             const uint32_t ko = k * UK * 4;  // 32 B inside the 128 B swizzle row
             const uint64_t dah = make_desc_k(sah + ko), dal = make_desc_k(sal + ko);
             const uint64_t dbh = make_desc_k(sbh + ko), dbl = make_desc_k(sbl + ko);
-            umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);  // small terms first
+            umma_tf32(tmem_d, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);  // small terms first
             umma_tf32(tmem_d, dah, dbl, idesc, 1u);
             umma_tf32(tmem_d, dah, dbh, idesc, 1u);
           }
           umma_commit(&empty[stage]);
-          if (kb == kblocks - 1) umma_commit(&tfull[as]);
+          if (kb == kb1 - 1) umma_commit(&tfull[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         ++iter;
@@ -162,9 +183,9 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     uint8_t* buf = smem_out + (warp - 2) * OUT_BUF_BYTES;
     int iter = 0;
     bool pending = false;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
-      if (skip_tile(m0, n0)) continue;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      int m0, n0, kb0, kb1;
+      if (!unit(u, m0, n0, kb0, kb1)) continue;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
@@ -173,7 +194,7 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
-        const bool live = row0 < a.M && col0 < a.N && !(a.lower_only && col0 > row0 + 31);
+        const bool live = row0 < a.M && col0 < a.N && !(lower_only && col0 > row0 + 31);
         if (!live) continue;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
@@ -191,7 +212,8 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_reduce_add_2d(&map_c, buf, col0, row0);
+          if (a.flags & TG_STORE) tma_store_2d(&map_c, buf, col0, row0);
+          else tma_reduce_add_2d(&map_c, buf, col0, row0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         pending = true;
@@ -272,8 +294,16 @@ int make_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
 
 // C[M,N] += alpha * (Ah + Al)[M,Kd] * (Bh + Bl)[N,Kd]^T   (3xTF32).  All bases 16 B aligned, lds % 4 == 0.
 int tgemm_nt(const float* Ah, const float* Al, int64_t lda, const float* Bh, const float* Bl, int64_t ldb, float* C,
-             int64_t ldc, int M, int N, int Kd, float alpha, int lower_only, cudaStream_t st) {
+             int64_t ldc, int M, int N, int Kd, float alpha, int flags, cudaStream_t st, int kchain) {
   if (M <= 0 || N <= 0 || Kd <= 0) return LCB_OK;
+  const int kblocks = (int)ceil_div(Kd, BK);
+  const int kcb = kchain > 0 ? (int)std::max<int64_t>(1, kchain / BK) : kblocks;
+  const int nchunks = (int)ceil_div(kblocks, kcb);
+  if (nchunks > 1 && (flags & TG_STORE)) {
+    // several chains per tile are combined by the L2 reduce-add: start from zero
+    LCB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+    flags &= ~TG_STORE;
+  }
   CUtensorMap mah, mal, mbh, mbl, mc;
   int rc;
   if ((rc = make_map_f32(&mah, Ah, M, Kd, lda, BK, BM)) != LCB_OK) return rc;
@@ -282,10 +312,11 @@ int tgemm_nt(const float* Ah, const float* Al, int64_t lda, const float* Bh, con
   if ((rc = make_map_f32(&mbl, Bl, N, Kd, ldb, BK, BN)) != LCB_OK) return rc;
   if ((rc = make_map_f32(&mc, C, M, N, ldc, 32, 32)) != LCB_OK) return rc;
   TgArgs a{};
-  a.M = M; a.N = N; a.Kd = Kd; a.alpha = alpha; a.lower_only = lower_only;
+  a.M = M; a.N = N; a.Kd = Kd; a.alpha = alpha; a.flags = flags;
   a.tiles_m = (int)ceil_div(M, BM); a.tiles_n = (int)ceil_div(N, BN);
+  a.kcb = kcb; a.nchunks = nchunks;
   LCB_CUDA(cudaFuncSetAttribute(tgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const int tiles = a.tiles_m * a.tiles_n;
+  const int tiles = a.tiles_m * a.tiles_n * nchunks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   tgemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, a);
   LCB_LAUNCH_CHECK();
@@ -302,3 +333,39 @@ int split_tf32(const float* in, int64_t ld_in, int rows, int cols, float* hi, fl
 }
 
 }  // namespace lcb
+
+using namespace lcb;
+
+namespace lcb {
+static std::atomic<int> g_gemm_mode{1};
+int gemm_mode() { return g_gemm_mode.load(std::memory_order_relaxed); }
+}  // namespace lcb
+
+extern "C" int lcb_set_gemm_mode(int mode) {
+  return g_gemm_mode.exchange(mode ? 1 : 0, std::memory_order_relaxed);
+}
+
+extern "C" size_t lcb_tgemm_ws_bytes(int64_t m, int64_t n, int64_t kd) {
+  return (size_t)(2 * (m + n) * kd + 64) * sizeof(float);
+}
+
+extern "C" int lcb_tgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
+                            int64_t n, int64_t kd, float alpha, int accumulate, int kchain, void* ws, size_t ws_bytes,
+                            void* stream) {
+  LCB_REQUIRE(A && B && C && m > 0 && n > 0 && kd > 0, "lcb_tgemm_nt: bad arguments");
+  LCB_REQUIRE(kd % 4 == 0 && tg_ok(C, ldc), "lcb_tgemm_nt: kd and ldc must be multiples of 4, C 16-byte aligned");
+  if (ws == nullptr || ws_bytes < lcb_tgemm_ws_bytes(m, n, kd) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("lcb_tgemm_nt: 16-byte aligned workspace of %zu bytes needed", lcb_tgemm_ws_bytes(m, n, kd));
+    return LCB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ah = static_cast<float*>(ws);
+  float* al = ah + m * kd;
+  float* bh = al + m * kd;
+  float* bl = bh + n * kd;
+  int rc = split_tf32(A, lda, (int)m, (int)kd, ah, al, kd, 0, st);
+  if (rc != LCB_OK) return rc;
+  rc = split_tf32(B, ldb, (int)n, (int)kd, bh, bl, kd, 0, st);
+  if (rc != LCB_OK) return rc;
+  return tgemm_nt(ah, al, kd, bh, bl, kd, C, ldc, (int)m, (int)n, (int)kd, alpha, accumulate ? 0 : TG_STORE, st, kchain);
+}

@@ -157,7 +157,7 @@ def gptaq_p(dxxt, U, alpha):
     L = _lib.lib()
     k = U.shape[0]
     P = torch.empty_like(U)
-    ws_bytes = k * k * 4
+    ws_bytes = L.lcb_gptaq_p_ws_bytes(k)
     ws = _ws(ws_bytes, U.device)
     with torch.cuda.device(U.device):
         rc = L.lcb_gptaq_p(_ptr(P), _ptr(dxxt), _ptr(U), k, float(alpha), _ptr(ws), ws_bytes, _stream(U.device))
@@ -233,3 +233,30 @@ def apply_mask(W, mask):
         rc = _lib.lib().lcb_apply_mask(_ptr(W), _wdt(W), _ptr(m), W.numel(), _stream(W.device))
     _lib.check(rc, "lcb_apply_mask")
     return W
+
+
+def set_gemm_mode(mode):
+    """Solver GEMM precision for every later call: 1 = tcgen05 3xTF32 (default), 0 = exact fp32 FFMA.
+    Returns the previous mode."""
+    return int(_lib.lib().lcb_set_gemm_mode(int(mode)))
+
+
+def tgemm_nt(A, B, C=None, alpha=1.0, accumulate=False, kchain=0):
+    """C (+)= alpha * A @ B^T on the tcgen05 3xTF32 path (fp32 row-major operands)."""
+    _need_cuda(A, B, C)
+    L = _lib.lib()
+    m, kd = A.shape
+    n = B.shape[0]
+    assert B.shape[1] == kd and A.dtype == torch.float32 and B.dtype == torch.float32
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    if C is None:
+        assert not accumulate
+        C = torch.empty((m, n), dtype=torch.float32, device=A.device)
+    assert C.stride(1) == 1 and C.dtype == torch.float32
+    ws_bytes = L.lcb_tgemm_ws_bytes(m, n, kd)
+    ws = _ws(ws_bytes, A.device)
+    with torch.cuda.device(A.device):
+        rc = L.lcb_tgemm_nt(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C), C.stride(0), m, n, kd, float(alpha),
+                            1 if accumulate else 0, int(kchain), _ptr(ws), ws_bytes, _stream(A.device))
+    _lib.check(rc, "lcb_tgemm_nt")
+    return C
