@@ -93,11 +93,52 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- ours
+def hessian_executed_fraction(K, BM=128, BN=256):
+    """share of the K x K tile grid the symmetric-half kernel actually computes (hessian.cu launch_xtx)"""
+    tm, tn = (K + BM - 1) // BM, (K + BN - 1) // BN
+    return sum(tn - (mt * BM) // BN for mt in range(tm)) / float(tm * tn)
+
+
+FQ_CASES = [
+    ("int4_g128_asym", dict(type="int", format="int4", group_size=128, axes=-1, zero_point=True), 4),
+    ("int8_token", dict(type="int", format="int8", group_size=-1, axes=-1, zero_point=False), 4),
+    ("mxfp4_g32", dict(type="mx", format="fp4_e2m1", group_size=32, axes=-1, zero_point=False), 4),
+    ("mxfp8_g32", dict(type="mx", format="fp8_e4m3", group_size=32, axes=-1, zero_point=False), 4),
+    ("nvfp4_g16", dict(type="nvfp", format="fp4_e2m1", group_size=16, axes=-1, zero_point=False), 6),
+]
+
+
+def fake_quant_bandwidth(lc, torch, dev, hbm_gbs):
+    """Second half of the metric: fused fake-quant HBM GB/s on a [65536, 3072] bf16 tensor (403 MB, larger
+    than L2).  Algorithmic bytes per element: 4 (read + write bf16); NVFP4 6 (the whole-tensor amax needs
+    a first pass, ref: nvfp_quant.py:87)."""
+    g = torch.Generator(device=dev).manual_seed(2)
+    x = (0.02 * torch.randn(8 * 8192, 3072, generator=g, device=dev)).to(torch.bfloat16)
+    out = {}
+    for name, cfg, bpe in FQ_CASES:
+        q = lc.FakeQuantizer.build(dict(cfg, is_profile=False)).to(dev)
+        q.check_nan = False   # the NaN-scale assert (int_quant.py:165) is a host sync; checked in the tests
+        for _ in range(3):
+            q(x)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            q(x)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 10
+        gbs = x.numel() * bpe / ms / 1e6
+        out[name] = {"GBs": gbs, "frac_of_hbm_peak": gbs / hbm_gbs, "bytes_per_elem": bpe, "ms": ms}
+    del x
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import llm_compressor_b200 as lc
-    from llm_compressor_b200 import _lib, ops, solvers
+    from llm_compressor_b200 import _lib, ops, parallel, solvers
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -117,83 +158,84 @@ def run_ours(args):
     acts = []
     for gi, (K, _) in enumerate(GROUPS):
         acts.append(xbuf[offs[gi]: offs[gi] + T_total * K].view(N_SAMPLES, SEQ_LEN, K))
-    my_samples = list(range(rank, N_SAMPLES, world))
+    my_samples = parallel.sample_shard(N_SAMPLES)
 
+    # weights: one stacked [sum N, K] bf16 matrix per sequential group (q/k/v and gate/up share their input)
     def make_weights(host):
         ws = []
         gw = torch.Generator(device=dev).manual_seed(1)
         for layer in range(args.layers):
-            lw = {}
+            lw = []
             for K, lins in GROUPS:
-                for name, N in lins:
-                    w = (0.02 * torch.randn(N, K, generator=gw, device=dev)).to(torch.bfloat16)
-                    if host:
-                        hw = torch.empty((N, K), dtype=torch.bfloat16, pin_memory=True)
-                        hw.copy_(w)
-                        w = hw
-                    lw[name] = w
+                ntot = sum(N for _, N in lins)
+                w = (0.02 * torch.randn(ntot, K, generator=gw, device=dev)).to(torch.bfloat16)
+                if host:
+                    hw = torch.empty((ntot, K), dtype=torch.bfloat16, pin_memory=True)
+                    hw.copy_(w)
+                    w = hw
+                lw.append(w)
             ws.append(lw)
         return ws
 
     weights_dev = make_weights(host=False)
     weights_host = make_weights(host=True)
-
-    def quantizer():
-        return lc.FakeQuantizer.build(WCFG).to(dev)
+    out_host = [[torch.empty(w.shape, dtype=w.dtype, pin_memory=True) for w in lw] for lw in weights_host]
+    copy_stream = torch.cuda.Stream(device=dev)
 
     class Lin(torch.nn.Module):
         def __init__(self, w):
             super().__init__()
             self.weight = torch.nn.Parameter(w, requires_grad=False)
-
-    hess_ms = []  # (flops, ms) per accumulated Hessian
+            self.weight_quantizer = lc.FakeQuantizer.build(WCFG).to(dev)
 
     def one_model(from_host):
-        """One step. Returns the list of (start, end) CUDA events of every Hessian accumulation."""
+        """One step. Returns the (start, end, flops) CUDA events of every Hessian accumulation."""
         evs = []
+        cur = torch.cuda.current_stream(dev)
+        staged = {}
+
+        def prefetch(layer, gi):  # H2D of one group's weights on the copy stream (pinned -> HBM)
+            if not from_host or layer >= args.layers:
+                return
+            with torch.cuda.stream(copy_stream):
+                w = weights_host[layer][gi].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            staged[(layer, gi)] = (w, ev)
+
+        prefetch(0, 0)
         for layer in range(args.layers):
-            src = weights_host[layer] if from_host else weights_dev[layer]
             for gi, (K, lins) in enumerate(GROUPS):
+                nxt = (layer, gi + 1) if gi + 1 < len(GROUPS) else (layer + 1, 0)
+                prefetch(*nxt)
                 H = torch.zeros(K, K, device=dev)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 X = acts[gi]
-                if world == 1:
-                    n = 0
-                    for j in my_samples:  # one hook call per calibration sample, like the reference
-                        n = ops.hessian_accum_raw(H, X[j], n)
-                    ops.hessian_finalize(H, 2.0 / n, True)
-                else:
-                    n = 0
-                    for j in my_samples:  # raw partial sums, reduced over NVLink, scaled once
-                        n = ops.hessian_accum_raw(H, X[j], n)
-                    dist.all_reduce(H)
-                    ops.hessian_finalize(H, 2.0 / N_SAMPLES, True)
+                n = 0
+                for j in my_samples:  # one hook call per calibration sample, like the reference
+                    n = ops.hessian_accum_raw(H, X[j], n)
+                n = parallel.reduce_hessian_(H, n)  # raw partial sums over NVLink (no-op on 1 GPU)
+                ops.hessian_finalize(H, 2.0 / n, True)
                 e1.record()
-                evs.append((e0, e1, 2.0 * SEQ_LEN * K * K * len(my_samples)))
+                evs.append((e0, e1, 2.0 * SEQ_LEN * K * K * len(my_samples), K))
                 fac = solvers.factorize(H, WCFG["group_size"], actorder=True, percdamp=0.01)
                 del H
-                for name, N in lins:
-                    w = src[name]
-                    if from_host:
-                        w = w.to(dev, non_blocking=True)
-                    rows = slice(0, N)
-                    if world > 1:  # rows are independent given U: shard them
-                        per = (N + world - 1) // world
-                        rows = slice(rank * per, min(N, (rank + 1) * per))
-                    lin = Lin(w[rows].clone() if (world > 1 or not from_host) else w)
-                    lin.weight_quantizer = quantizer()
-                    solvers.update_weight(lin, dev, block_size=128, percdamp=0.01, actorder=True, factor=fac)
-                    out = lin.weight.data
-                    if world > 1:
-                        parts = [torch.empty_like(out) for _ in range(world)]
-                        dist.all_gather(parts, out.contiguous())
-                        out = torch.cat(parts, 0)[:N]
-                    if from_host:  # device -> pinned host buffer, asynchronous on the compute stream
-                        key = name + "_out"
-                        if key not in weights_host[layer]:
-                            weights_host[layer][key] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-                        weights_host[layer][key].copy_(out, non_blocking=True)
+                if from_host:
+                    w, ev = staged.pop((layer, gi))
+                    cur.wait_event(ev)
+                    w.record_stream(cur)
+                else:
+                    w = weights_dev[layer][gi]
+                ntot = w.shape[0]
+                rows = parallel.row_shard(ntot)  # rows are independent given U: shard them over ranks
+                # the group's Linears as one stacked problem (solvers.update_weights_shared does this stacking
+                # for separate modules; here the weights are stored stacked)
+                lin = Lin(w[rows])
+                solvers.update_weight(lin, dev, block_size=128, percdamp=0.01, actorder=True, factor=fac)
+                out = parallel.gather_rows(lin.weight.data, ntot)
+                if from_host:  # device -> pinned host buffer, asynchronous
+                    out_host[layer][gi].copy_(out, non_blocking=True)
         return evs
 
     def timed(from_host, steps):
@@ -224,41 +266,59 @@ def run_ours(args):
         sampler.start()
     ms, evs, launches = timed(False, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    hess_flops = sum(f for _, _, f in evs)
-    hess_ms_total = sum(a.elapsed_time(b) for a, b, _ in evs)
+    hess_flops = sum(f for _, _, f, _ in evs)
+    hess_exec = sum(f * hessian_executed_fraction(K) for _, _, f, K in evs)
+    hess_ms_total = sum(a.elapsed_time(b) for a, b, _, _ in evs)
     n_hess_launch = len(evs) * len(my_samples)
 
-    e2e_ms, _, _ = timed(True, max(1, min(args.steps, 2)))
     e2e_steps = max(1, min(args.steps, 2))
+    one_model(True)  # warm the pinned-memory / copy-stream path
+    e2e_ms, _, _ = timed(True, e2e_steps)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak_tf, hbm_gbs, src = peaks()
+    fq = fake_quant_bandwidth(lc, torch, dev, hbm_gbs) if not args.no_fake_quant else None
     achieved = hess_flops / (hess_ms_total * 1e-3) / 1e12
+    executed = hess_exec / (hess_ms_total * 1e-3) / 1e12
     wbytes = sum(N * K * 2 for K, lins in GROUPS for _, N in lins) * args.layers
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "hessian_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
     cpu = cpu_baseline_sample() if not args.no_cpu_baseline else None
     out = {
         "metric": "GPTQ W4g128 sec/model (Llama-3.2-3B)", "value": ms / 1e3 / args.steps, "unit": "s/model",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (Hessian), f32 (solver)",
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16 x bf16 -> f32 (Hessian, tcgen05), 3xTF32 -> f32 (solver contractions, tcgen05), f32 (quantizer)",
         "data": "synthetic",
         "config": {"workload": "Llama-3.2-3B shapes (28 layers x 7 Linears), GPTQ int4-g[128]-rw act-order, "
                                "synthetic 128x2048-token bf16 activations per Linear input, random-init bf16 weights",
                    "calibration_forwards": "outside the path (north_star)", "layers": args.layers, "hessians_per_layer": 4,
                    "hessian_form": "raw sums of the symmetric half per sample + one finalize (2/n, mirror) per Hessian",
+                   "solve_form": "q/k/v and gate/up stacked into one [sum N, K] solve per shared Hessian",
                    "l2_note": "activation buffer 4.3 GB and Hessians 38-268 MB: inputs larger than L2",
                    "parallelism": "samples sharded + all-reduce(H), rows sharded + all-gather" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_ms / 1e3 / e2e_steps, "unit": "s/model", "h2d_bytes_per_step": wbytes,
                 "d2h_bytes_per_step": wbytes,
-                "note": "weights in pinned host memory; activations are produced on the device in the reference flow too"},
+                "note": "weights in pinned host memory, H2D prefetched one group ahead on a copy stream, results "
+                        "copied back to pinned host memory; activations are produced on the device in the "
+                        "reference flow too"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "hessian_umma_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": src + " sustained bf16",
+                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                     "peak_source": src + " sustained bf16 (MEASURED_PEAKS.json)",
+                     "note": "achieved counts the ALGORITHMIC 2*T*K^2 flop per launch (SURVEY 8d); the kernel "
+                             "computes only the tiles touching the upper triangle, so frac can exceed 1 -- "
+                             "executed_* is the tensor-pipe rate of the MMAs actually issued",
+                     "executed_tflops": executed, "executed_frac": executed / peak_tf,
                      "launches": n_hess_launch, "avg_launch_ms": hess_ms_total / max(n_hess_launch, 1),
                      "stage_share_of_step": hess_ms_total / ms},
+        "fake_quant": fq,
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))
@@ -343,6 +403,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--no-fake-quant", action="store_true", help="skip the fake-quant bandwidth section")
     ap.add_argument("--layers", type=int, default=N_LAYERS,
                     help="decoder layers per step (default: the full 28-layer model; smaller only for profiling runs, "
                          "the JSON line then says so in config.layers)")

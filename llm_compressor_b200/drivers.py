@@ -163,17 +163,21 @@ def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, da
                 layer(inps[j].unsqueeze(0), **layer_kwargs)
             handle.remove()
             H = solvers.finalize_hessian(fq)
-            factors = {}
+            by_group = {}
             for name in subset:
                 wq = subset[name].weight_quantizer
                 wq.mse = mse
                 key = wq.group_size if wq.group_size not in (0, -1) else -1
-                if key not in factors:
-                    factors[key] = solvers.factorize(H, wq.group_size, actorder=True, percdamp=0.01)
-                solvers.update_weight(layer=subset[name], device=device, block_size=128, percdamp=0.01, actorder=True,
-                                      factor=factors[key])
+                by_group.setdefault(key, []).append(name)
+            for key, members in by_group.items():
+                gs = subset[members[0]].weight_quantizer.group_size
+                factor = solvers.factorize(H, gs, actorder=True, percdamp=0.01)
+                # one stacked [sum N, K] solve for the Linears that share this factor
+                solvers.update_weights_shared([subset[n] for n in members], device, factor, block_size=128)
+                del factor
+            for name in subset:
                 del subset[name].weight_quantizer
-            del H, factors
+            del H
         for j in range(n_samples):
             outs[j] = _first(layer(inps[j].unsqueeze(0), **layer_kwargs))
         layers[i] = layer.cpu()

@@ -1,0 +1,97 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU, torch.distributed.
+
+The reference is single-device; these are the two natural shardings of its layer loop:
+
+  * calibration samples are sharded over ranks (`sample_shard`).  Each rank's hooks accumulate RAW sums
+    S_r = sum_j X_j^T X_j (solvers.HESSIAN_MODE == "lazy"); `reduce_hessian_` all-reduces them and the
+    single finalize applies 2 / n_total -- algebraically the running mean of ref: gptq/core.py:113-119.
+  * Linear output rows are sharded for the solve (`row_shard`): rows are independent given U, the
+    act-order permutation and per-row / per-group parameters (ref: gptq/core.py:226-265 touches rows
+    only through W[:, cols]); `gather_rows` all-gathers the updated rows so every rank holds the full
+    layer for the next calibration forward.  Statistics that span rows are reduced explicitly:
+    NVFP's per-matrix amax (ref: nvfp_quant.py:87) with `allreduce_max_`, SparseGPT's per-block
+    threshold and the RIA / magnitude global thresholds need the gathered scores (not sharded here).
+
+Only collectives and index arithmetic live here (they work with NCCL on CUDA tensors and with gloo on
+CPU tensors, which is how tests/test_parallel_cpu.py covers the N > 1 logic without a GPU); every
+numeric stage stays in liblcb200.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size) of the default process group; (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def sample_shard(n_samples, rank=None, world_size=None):
+    """Calibration samples of this rank: rank, rank + world, ... (round-robin keeps the shards balanced
+    when n_samples is not a multiple of world)."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    return list(range(rank, n_samples, world_size))
+
+
+def row_shard(n_rows, rank=None, world_size=None):
+    """Contiguous slice of Linear output rows owned by this rank (ceil-divided; trailing ranks may be short
+    or empty)."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    per = (n_rows + world_size - 1) // world_size
+    lo = min(n_rows, rank * per)
+    return slice(lo, min(n_rows, lo + per))
+
+
+def reduce_hessian_(H, nsamples, dxxt=None, group=None):
+    """all-reduce(SUM) of the raw per-rank sums (and of the per-rank sample count).  Returns n_total; the
+    caller finalises ONCE with scale 2 / n_total (ops.hessian_finalize)."""
+    r, w = world()
+    if w == 1:
+        return nsamples
+    dist.all_reduce(H, op=dist.ReduceOp.SUM, group=group)
+    if dxxt is not None:
+        dist.all_reduce(dxxt, op=dist.ReduceOp.SUM, group=group)
+    n = torch.tensor([float(nsamples)], dtype=torch.float64, device=H.device)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+    return int(round(float(n.item())))
+
+
+def reduce_rownorm_(scaler_raw, nsamples, group=None):
+    """Wanda / RIA row norms (ref: wanda/core.py:92-105) kept as raw sums sum_t X[t,:]^2 per rank:
+    all-reduce(SUM), then the caller divides by n_total."""
+    r, w = world()
+    if w == 1:
+        return nsamples
+    dist.all_reduce(scaler_raw, op=dist.ReduceOp.SUM, group=group)
+    n = torch.tensor([float(nsamples)], dtype=torch.float64, device=scaler_raw.device)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+    return int(round(float(n.item())))
+
+
+def allreduce_max_(t, group=None):
+    """all-reduce(MAX), e.g. of lcb_nvfp_global_amax's result when a matrix is row-sharded."""
+    r, w = world()
+    if w > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
+
+
+def gather_rows(local_rows, n_rows, group=None):
+    """Reassemble [n_rows, k] from the per-rank row slices of `row_shard` (all ranks get the result)."""
+    r, w = world()
+    if w == 1:
+        return local_rows
+    per = (n_rows + w - 1) // w
+    k = local_rows.shape[1]
+    padded = local_rows
+    if local_rows.shape[0] != per:  # short / empty trailing shard: pad so that all_gather sees equal shapes
+        padded = torch.zeros((per, k), dtype=local_rows.dtype, device=local_rows.device)
+        padded[: local_rows.shape[0]] = local_rows
+    out = torch.empty((w * per, k), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    return out[:n_rows]

@@ -104,23 +104,12 @@ def factorize(H, group_size, actorder=True, percdamp=0.01, dXXT=None, alpha=0.25
     return Factor(dead, perm, invperm, col_perm, U, P, group_size)
 
 
-def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, factor=None):
-    q = layer.weight_quantizer
-    W = layer.weight.data.clone()
-    if _is_conv1d(layer):
-        W = W.t()
-    W = W.float().contiguous()
+def _solve(q, W, factor, block_size):
+    """GPTQ / GPTAQ solve of one fp32 weight matrix W [N, K] (rows = outputs) with quantizer q and a
+    ready Factor; returns the dequantised result [N, K] fp32 in the original column order."""
     keep = (W != 0).to(torch.uint8)
     N, K = W.shape
-    group_size = q.group_size  # read before find_params mutates -1 (ref: gptq/core.py:171)
-
-    if factor is None:
-        H = finalize_hessian(q)
-        dXXT = q.dXXT if alpha is not None else None
-        factor = factorize(H, group_size, actorder, percdamp, dXXT, alpha if alpha is not None else 0.25)
-    for attr in ("H", "dXXT"):
-        if hasattr(q, attr):
-            delattr(q, attr)
+    group_size = factor.group_size
     W.masked_fill_(factor.dead.unsqueeze(0), 0)
 
     per_col = group_size in (0, -1)
@@ -151,9 +140,61 @@ def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, fa
             Q = Q[:, factor.invperm]
         else:
             Q = Q.reshape(N, K // group_size, group_size)[:, factor.invperm, :].reshape(N, K)
+    return Q
+
+
+def _layer_w(layer):
+    W = layer.weight.data.clone()
+    if _is_conv1d(layer):
+        W = W.t()
+    return W.float().contiguous()
+
+
+def _store_w(layer, Q):
     if _is_conv1d(layer):
         Q = Q.t()
     layer.weight.data = Q.reshape(layer.weight.shape).to(layer.weight.data.dtype)
+
+
+def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, factor=None):
+    q = layer.weight_quantizer
+    W = _layer_w(layer)
+    group_size = q.group_size  # read before find_params mutates -1 (ref: gptq/core.py:171)
+    if factor is None:
+        H = finalize_hessian(q)
+        dXXT = q.dXXT if alpha is not None else None
+        factor = factorize(H, group_size, actorder, percdamp, dXXT, alpha if alpha is not None else 0.25)
+    for attr in ("H", "dXXT"):
+        if hasattr(q, attr):
+            delattr(q, attr)
+    _store_w(layer, _solve(q, W, factor, block_size))
+
+
+def update_weights_shared(layers, device, factor, block_size=128):
+    """Solve several Linears that share one Factor (q/k/v, gate/up: same input, same H) as ONE stacked
+    [sum N_i, K] problem.  Rows are independent given U, the permutation and row-wise quantiser
+    parameters, so the result equals calling update_weight on each layer (ref: gptq/core.py:129-137 loops
+    over them one by one); it just runs K/128 block steps once instead of once per Linear.
+    Quantisers with a per-matrix statistic (NVFP's global amax, per-tensor scales) are not stacked."""
+    layers = list(layers)
+    q0 = layers[0].weight_quantizer
+    stackable = len(layers) > 1 and type(q0).__name__ != "NVFPQuantizer" and q0.group_size != 0 and q0.axes == -1 \
+        and not any(_is_conv1d(l) for l in layers) and all(type(l.weight_quantizer) is type(q0) for l in layers)
+    if not stackable:
+        for l in layers:
+            _update_weight(l, device, block_size, 0.01, True, factor=factor)
+        return
+    sizes = [l.weight.shape[0] for l in layers]
+    W = torch.cat([l.weight.data for l in layers], 0).float().contiguous()
+    for l in layers:
+        for attr in ("H", "dXXT"):
+            if hasattr(l.weight_quantizer, attr):
+                delattr(l.weight_quantizer, attr)
+    Q = _solve(q0, W, factor, block_size)
+    o = 0
+    for l, n in zip(layers, sizes):
+        _store_w(l, Q[o:o + n])
+        o += n
 
 
 def update_weight(layer, device, block_size=128, percdamp=0.01, actorder=False, factor=None):

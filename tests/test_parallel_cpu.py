@@ -1,0 +1,129 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU partitioning logic (llm_compressor_b200/parallel.py).
+
+The numeric stages need a GPU, so here the CPU oracle plays their role: what is checked is that
+sample-sharded raw Hessian sums + all-reduce + one finalize equal the reference's running mean, and
+that row-sharded solves + all-gather equal the unsharded solve bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, ret):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = globals()[fn](rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def _inputs():
+    import oracle as orc
+    rng = np.random.default_rng(3)
+    n_samples, T, K, N = 5, 96, 256, 96     # odd sample count: unbalanced shards
+    X = orc.bf16_round(rng.standard_normal((n_samples, T, K), dtype=np.float32) * np.exp(0.5 * rng.standard_normal(K)).astype(np.float32))
+    W = orc.bf16_round(0.02 * rng.standard_normal((N, K), dtype=np.float32))
+    return orc, X, W
+
+
+def _hessian_case(rank, world):
+    from llm_compressor_b200 import parallel
+    orc, X, W = _inputs()
+    n_samples, T, K = X.shape
+    mine = parallel.sample_shard(n_samples)
+    S = np.zeros((K, K), np.float64)
+    for j in mine:  # raw sums, as the lazy hook accumulates them
+        S += X[j].astype(np.float64).T @ X[j].astype(np.float64)
+    H = torch.from_numpy(S.astype(np.float32))
+    n_tot = parallel.reduce_hessian_(H, len(mine))
+    H = H.numpy() * np.float32(2.0 / n_tot)
+    Href = np.zeros((K, K), np.float32)
+    n = 0
+    for j in range(n_samples):  # the reference's running mean over ALL samples
+        n = orc.hessian_accum(Href, X[j], n)
+    rel = float(np.linalg.norm(H - Href) / np.linalg.norm(Href))
+    return dict(n_tot=n_tot, mine=mine, rel=rel, H=H)
+
+
+def _rows_case(rank, world):
+    from llm_compressor_b200 import parallel
+    orc, X, W = _inputs()
+    n_samples, T, K = X.shape
+    N = W.shape[0]
+    H = np.zeros((K, K), np.float32)
+    n = 0
+    for j in range(n_samples):
+        n = orc.hessian_accum(H, X[j], n)
+    cfg = dict(type="int", format="int4", group_size=128, axes=-1, zero_point=False, is_profile=False)
+    full = orc.gptq_update(W, H.copy(), cfg)
+    rows = parallel.row_shard(N)
+    part = orc.gptq_update(W[rows], H.copy(), cfg)     # rows are independent given H
+    got = parallel.gather_rows(torch.from_numpy(part), N).numpy()
+    # NVFP: the per-matrix amax must be reduced over the row shards
+    amax = torch.tensor([float(np.abs(W[rows]).max())])
+    parallel.allreduce_max_(amax)
+    return dict(equal=bool(np.array_equal(got, full)), rows=(rows.start, rows.stop),
+                amax_ok=bool(float(amax) == float(np.abs(W).max())))
+
+
+def _ragged_case(rank, world):
+    from llm_compressor_b200 import parallel
+    N, K = 7, 12   # 7 rows over 3 ranks: 3 + 3 + 1
+    full = torch.arange(N * K, dtype=torch.float32).reshape(N, K)
+    rows = parallel.row_shard(N)
+    got = parallel.gather_rows(full[rows].clone(), N)
+    return bool(torch.equal(got, full))
+
+
+def test_sample_sharded_hessian_allreduce_matches_running_mean():
+    res = _run("_hessian_case", 2)
+    assert res[0]["n_tot"] == res[1]["n_tot"] == 5
+    assert sorted(res[0]["mine"] + res[1]["mine"]) == list(range(5))
+    assert res[0]["rel"] < 1e-6 and res[1]["rel"] < 1e-6
+    assert np.array_equal(res[0]["H"], res[1]["H"])
+
+
+def test_row_sharded_solve_allgather_is_bit_identical():
+    res = _run("_rows_case", 2)
+    assert all(r["equal"] and r["amax_ok"] for r in res)
+    assert res[0]["rows"] == (0, 48) and res[1]["rows"] == (48, 96)
+
+
+def test_ragged_row_shards_world3():
+    assert all(_run("_ragged_case", 3))
+
+
+def test_shard_index_math_single_process():
+    from llm_compressor_b200 import parallel
+    assert parallel.world() == (0, 1)
+    assert parallel.sample_shard(10, 1, 4) == [1, 5, 9]
+    sl = [parallel.row_shard(1024, r, 8) for r in range(8)]
+    assert [s.start for s in sl] == list(range(0, 1024, 128)) and sl[-1].stop == 1024
+    sl = [parallel.row_shard(5, r, 4) for r in range(4)]
+    assert [(s.start, s.stop) for s in sl] == [(0, 2), (2, 4), (4, 5), (5, 5)]

@@ -321,3 +321,26 @@ def test_masks_vs_oracle_seeded(N, K):
     m = ops.mask_wanda(Wd, s.to(DEV), 0.5)
     ops.apply_mask(Wd, m)
     assert float((Wd == 0).float().mean()) >= 0.5
+
+
+def test_stacked_solve_equals_per_linear(gemm_mode):
+    """q/k/v share H: solving them as one stacked [sum N, K] problem (solvers.update_weights_shared) gives
+    the same weights as the reference's one-Linear-at-a-time loop (ref: gptq/core.py:129-137)."""
+    from llm_compressor_b200 import solvers
+    K, Ns, T = 1024, (512, 128, 128), 1024
+    cfg = dict(type="int", format="int4", group_size=128, axes=-1, zero_point=False, is_profile=False)
+    g = torch.Generator().manual_seed(9)
+    X = (torch.randn(T, K, generator=g) * torch.exp(0.8 * torch.randn(K, generator=g))).to(torch.bfloat16)
+    H = torch.zeros(K, K, device=DEV)
+    _ops().hessian_add(H, X.to(DEV), 2.0 / 1, 0.0)
+    Ws = [(0.02 * torch.randn(n, K, generator=g)).to(torch.bfloat16) for n in Ns]
+    fac = solvers.factorize(H.clone(), 128, True, 0.01)
+    sep = []
+    for W in Ws:
+        lin = _layer(W, cfg)
+        solvers.update_weight(lin, DEV, actorder=True, factor=fac)
+        sep.append(lin.weight.data.clone())
+    lins = [_layer(W, cfg) for W in Ws]
+    solvers.update_weights_shared(lins, DEV, fac)
+    for a, l in zip(sep, lins):
+        assert torch.equal(a, l.weight.data)
