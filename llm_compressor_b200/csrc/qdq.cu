@@ -33,6 +33,10 @@ __device__ __forceinline__ void flag_nan_scale(const QdqArgs& a, float s) {
   if (a.status != nullptr && s != s) atomicOr(a.status, LCB_ST_NAN_SCALE);
 }
 
+}  // namespace lcb
+#include "qdq_stream.cuh"
+namespace lcb {
+
 template <typename T, int N>
 __device__ __forceinline__ void stats_of(const float (&v)[N], float& mx, float& mn, float& amax) {
 #pragma unroll
@@ -705,6 +709,67 @@ static int launch_rowcta_fast(const QdqArgs& a, int kind, int64_t total, cudaStr
   }
 }
 
+template <int KIND>
+static int launch_stream_k(const QdqArgs& a, int lpg, int grid, cudaStream_t st) {
+  switch (lpg) {
+    case 1: qdq_stream_kernel<KIND, 1><<<grid, 256, 0, st>>>(a); break;
+    case 2: qdq_stream_kernel<KIND, 2><<<grid, 256, 0, st>>>(a); break;
+    case 4: qdq_stream_kernel<KIND, 4><<<grid, 256, 0, st>>>(a); break;
+    case 8: qdq_stream_kernel<KIND, 8><<<grid, 256, 0, st>>>(a); break;
+    case 16: qdq_stream_kernel<KIND, 16><<<grid, 256, 0, st>>>(a); break;
+    default: qdq_stream_kernel<KIND, 32><<<grid, 256, 0, st>>>(a); break;
+  }
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+// streaming kernels (qdq_stream.cuh): groups of 16 * 2^j <= 512 elements tiling the rows, 32 B aligned
+static bool stream_geometry(const QdqArgs& a, bool need_out) {
+  const int64_t lpg = a.group / 16;
+  return a.group % 16 == 0 && lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && a.cols == a.G * a.group &&
+         (reinterpret_cast<uintptr_t>(a.x) & 31) == 0 && (!need_out || (reinterpret_cast<uintptr_t>(a.out) & 31) == 0);
+}
+static int launch_stream(const QdqArgs& a, int kind, cudaStream_t st) {
+  const int lpg = (int)(a.group / 16);
+  const int64_t chunks = a.nrows * a.cols / 16;
+  LCB_REQUIRE(ceil_div(chunks, 512) < (int64_t)0x7fffffff, "lcb_qdq: tensor too large for one launch");
+  const int grid = (int)ceil_div(chunks, 512);  // flat: 2 x 256 chunks per CTA (see qdq_stream_kernel)
+  switch (kind) {
+    case FK_INT4: return launch_stream_k<FK_INT4>(a, lpg, grid, st);
+    case FK_INT8: return launch_stream_k<FK_INT8>(a, lpg, grid, st);
+    case FK_E2M1: return launch_stream_k<FK_E2M1>(a, lpg, grid, st);
+    case FK_E4M3: return launch_stream_k<FK_E4M3>(a, lpg, grid, st);
+    default: return launch_stream_k<FK_E5M2>(a, lpg, grid, st);
+  }
+}
+
+// long groups (per-token rows): one CTA per group, group % 16 == 0, 512 < group <= 16384, groups tiling the rows
+static bool rowstream_geometry(const QdqArgs& a) {
+  return a.group % 16 == 0 && a.group > 512 && a.group <= 16384 && a.cols == a.G * a.group &&
+         ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 31) == 0 &&
+         a.nrows * a.G < (int64_t)0x7fffffff;
+}
+template <int KIND>
+static int launch_rowstream_k(const QdqArgs& a, cudaStream_t st) {
+  const int cpg = (int)(a.group / 16);
+  const int grid = (int)(a.nrows * a.G);
+  const int cpt = cpg <= 256 ? 1 : (cpg <= 512 ? 2 : 4);
+  int threads = (int)ceil_div(ceil_div(cpg, cpt), 32) * 32;
+  if (cpt == 1) qdq_rowstream_kernel<KIND, 1><<<grid, threads, 0, st>>>(a);
+  else if (cpt == 2) qdq_rowstream_kernel<KIND, 2><<<grid, threads, 0, st>>>(a);
+  else qdq_rowstream_kernel<KIND, 4><<<grid, threads, 0, st>>>(a);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+static int launch_rowstream(const QdqArgs& a, int kind, cudaStream_t st) {
+  switch (kind) {
+    case FK_INT4: return launch_rowstream_k<FK_INT4>(a, st);
+    case FK_INT8: return launch_rowstream_k<FK_INT8>(a, st);
+    case FK_E2M1: return launch_rowstream_k<FK_E2M1>(a, st);
+    case FK_E4M3: return launch_rowstream_k<FK_E4M3>(a, st);
+    default: return launch_rowstream_k<FK_E5M2>(a, st);
+  }
+}
+
 template <typename T, bool P1>
 static int launch_rowwise(const QdqArgs& a, uint32_t* amax_key, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
@@ -714,6 +779,19 @@ static int launch_rowwise(const QdqArgs& a, uint32_t* amax_key, cudaStream_t st)
   const bool vec_ok = ptr_ok && (a.cols % VEC == 0) && (a.group % VEC == 0);
   const int64_t lpg = a.group / VEC;
   if constexpr (std::is_same<T, __nv_bfloat16>::value && P1) {
+    if (stream_geometry(a, false)) {
+      const int grid = (int)ceil_div(a.nrows * a.cols / 16, 1024);
+      switch (a.group / 16) {
+        case 1: nvfp_amax_stream_kernel<1><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 2: nvfp_amax_stream_kernel<2><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 4: nvfp_amax_stream_kernel<4><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 8: nvfp_amax_stream_kernel<8><<<grid, 256, 0, st>>>(a, amax_key); break;
+        case 16: nvfp_amax_stream_kernel<16><<<grid, 256, 0, st>>>(a, amax_key); break;
+        default: nvfp_amax_stream_kernel<32><<<grid, 256, 0, st>>>(a, amax_key); break;
+      }
+      LCB_LAUNCH_CHECK();
+      return LCB_OK;
+    }
     if (vec_ok && a.cols == a.G * a.group && lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0) {
       const int grid = grid_for(total, (int64_t)8 * (32 / (int)lpg) * 2, 8);
       switch (lpg) {
@@ -730,6 +808,8 @@ static int launch_rowwise(const QdqArgs& a, uint32_t* amax_key, cudaStream_t st)
   }
   if constexpr (std::is_same<T, __nv_bfloat16>::value && !P1) {
     const int kind = fast_kind(a);
+    if (kind >= 0 && a.find && a.apply && stream_geometry(a, true)) return launch_stream(a, kind, st);
+    if (kind >= 0 && a.find && a.apply && rowstream_geometry(a)) return launch_rowstream(a, kind, st);
     if (kind >= 0 && vec_ok) {
       if (lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0) return launch_subwarp_fast(a, kind, (int)lpg, total, st);
       if (a.group <= (int64_t)256 * VEC * 8) return launch_rowcta_fast(a, kind, total, st);

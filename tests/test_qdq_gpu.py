@@ -120,6 +120,9 @@ def test_oracle_bit_exact_seeded(case):
     if cfg["type"] == "int":
         got = codes.cpu().numpy().view(np.int8).astype(np.float32)
         assert np.array_equal(got, rcodes), "integer codes"
+    # the plain forward takes the streaming / fast kernels (no code output): same bits
+    y2 = q(x.to(_dev()))
+    assert same(to_f32_np(y2), ref), "forward (fast path): %d of %d differ" % (n_diff(to_f32_np(y2), ref), ref.size)
 
 
 def test_fp_codes_decode_to_grid_values():
@@ -203,3 +206,59 @@ def test_all_bf16_patterns_with_given_params_vs_oracle(cfgname):
     y = _build(cfg)(x, scales=s, zeros=z)
     ref, _, _, _ = orc.qdq(gio.bits_to_f32(bits), cfg, orc.BF16, scales=to_f32_np(s), zeros=to_f32_np(z))
     assert same(to_f32_np(y), ref), n_diff(to_f32_np(y), ref)
+
+
+STREAM_CFGS = [
+    ("int4_g128", _c("int", "int4", 128)), ("int4_g128_zp", _c("int", "int4", 128, zp=True)),
+    ("int8_g128_zp", _c("int", "int8", 128, zp=True)), ("int8_g16", _c("int", "int8", 16)),
+    ("int4_g512_zp", _c("int", "int4", 512, zp=True)),
+    ("fp4_g32_zp", _c("fp", "fp4_e2m1", 32, zp=True)), ("fp8e4m3_g64", _c("fp", "fp8_e4m3", 64)),
+    ("fp8e5m2_g128_zp", _c("fp", "fp8_e5m2", 128, zp=True)),
+    ("mxfp4", _c("mx", "fp4_e2m1", 32)), ("mxfp8", _c("mx", "fp8_e4m3", 32)), ("mxfp8e5m2", _c("mx", "fp8_e5m2", 32)),
+    ("mxfp4_zp", _c("mx", "fp4_e2m1", 32, zp=True)),
+    ("nvfp4", _c("nvfp", "fp4_e2m1", 16)), ("nvfp4_zp", _c("nvfp", "fp4_e2m1", 16, zp=True)),
+    ("int8_tok", _c("int", "int8", -1)), ("int4_tok_zp", _c("int", "int4", -1, zp=True)),
+    ("fp8e4m3_tok", _c("fp", "fp8_e4m3", -1)), ("fp4_tok_zp", _c("fp", "fp4_e2m1", -1, zp=True)),
+]
+
+
+def _stress_inputs(rows, cols, seed):
+    """bf16 inputs that walk the corners of the streaming kernels: wide dynamic range inside a group (fp8
+    sub-normal range), tiny groups (scale clamp 1e-5), exact zeros, all-equal groups, huge values, and a few
+    inf / NaN groups (non-finite parameters -> reference arithmetic branch)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, cols, generator=g)
+    x = x * torch.exp(3.0 * torch.randn(rows, cols, generator=g))          # ~ e^+-9 dynamic range
+    x[1] *= 1e-7                                                             # scales below the 1e-5 clamp
+    x[2] = 0.0
+    x[3] = 1.5
+    x[4] *= 1e30
+    x[5, ::7] = 0.0
+    x[6] = torch.round(x[6] * 4) / 4
+    x[7] = -x[7].abs()
+    xb = x.to(torch.bfloat16)
+    xb[8, 5] = float("inf")
+    xb[9, 100] = float("nan")
+    xb[10, 17] = float("-inf")
+    return xb
+
+
+@pytest.mark.parametrize("case", STREAM_CFGS, ids=[c[0] for c in STREAM_CFGS])
+@pytest.mark.parametrize("cols", [1024, 3072])
+def test_stream_kernels_match_generic_kernels_and_oracle(case, cols):
+    """Forward (streaming kernels, qdq_stream.cuh) == code-emitting generic kernels == CPU oracle, bit for bit,
+    on stress inputs; NaN scales are reported the same way (the reference asserts, int_quant.py:165)."""
+    name, cfg = case
+    x = _stress_inputs(64, cols, 1234 + cols)
+    q = _build(cfg)
+    q.check_nan = False
+    xd = x.to(_dev())
+    y_fast = q(xd)
+    y_gen, s, z, _ = q.quantize_with_codes(xd)
+    assert same(to_f32_np(y_fast), to_f32_np(y_gen)), "%d differ" % n_diff(to_f32_np(y_fast), to_f32_np(y_gen))
+    # finite rows against the oracle (rows 8-10 carry inf / NaN: NVFP's tensor-wide amax would poison all rows)
+    xf = x[:8].contiguous()
+    ref, _, _, _ = orc.qdq(xf.float().numpy(), cfg, orc.BF16)
+    q2 = _build(cfg)
+    q2.check_nan = False
+    assert same(to_f32_np(q2(xf.to(_dev()))), ref)
