@@ -74,46 +74,34 @@ __global__ void zero_strict_upper_kernel(float* A, int64_t k) {
   if (j < k && j > i) A[i * k + j] = 0.0f;
 }
 
-// One CTA (256 threads): Cholesky of the nb x nb diagonal block at A (ld) and the inverse of the
-// factor (`dinv` [NB x NB], turns the panel TRSM into a GEMM).  The 128 x 128 block lives in
-// registers, 8 x 8 per thread (thread (ty, tx) owns rows ty*8.., columns tx*8..).  Both phases are
-// blocked by 8: per panel one thread factors / inverts an 8 x 8 diagonal tile in registers, the
-// panel tiles are exchanged through shared memory and every other thread does 8x8x8 register
-// FMAs -- 16 panel steps of ~3 barriers instead of 128 latency-bound column steps.
-__global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, int nb, float* dinv, uint32_t* status) {
-  constexpr int PS = 9;                   // padded panel row stride
-  __shared__ float P[NB * PS];            // column panel  P[r][m] = L[r][p*8 + m]
-  __shared__ float XP[8 * (NB + 4)];      // row panel     XP[m][c] = X[k*8 + m][c]
-  __shared__ float dall[16][64];          // inverted diagonal tiles
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  float a[8][8], x[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int r = ty * 8 + i, cc = tx * 8 + c;
-      float v = (r == cc) ? 1.0f : 0.0f;  // identity padding for a short last block
-      if (r < nb && cc < nb) v = (cc <= r) ? A[(int64_t)r * ld + cc] : 0.0f;
-      a[i][c] = v;
-      x[i][c] = (r == cc) ? 1.0f : 0.0f;
-    }
-  bool bad = false;
+// Register-tiled 128 x 128 building blocks shared by the Cholesky kernels.  256 threads; thread (ty, tx)
+// owns the 8 x 8 tile at rows ty*8.., columns tx*8.. in registers.  Both phases are blocked by 8: per
+// panel one thread factors / inverts an 8 x 8 diagonal tile, the panel tiles are exchanged through
+// shared memory and every other thread does 8x8x8 register FMAs -- 16 panel steps of ~3 barriers
+// instead of 128 latency-bound column steps.
+constexpr int PS = 9;  // padded panel row stride
 
+// in: a = lower triangle (incl. diagonal) of an SPD block; out: a = its Cholesky factor L (upper tiles
+// zero), dall[p] = inverse of the p-th 8 x 8 diagonal tile of L.  P: NB * PS floats of scratch.
+__device__ __forceinline__ void factor_block(float (&a)[8][8], float* P, float (*dall)[64], bool& bad, int ty, int tx) {
   // ================= factorisation, right-looking over 16 panels of 8 columns
 #pragma unroll 1
   for (int p = 0; p < 16; ++p) {
     if (ty == p && tx == p) {
-      // unblocked Cholesky of the 8 x 8 diagonal tile, then its inverse
+      // unblocked Cholesky of the 8 x 8 diagonal tile, then its inverse.  One rsqrt (MUFU + one Newton
+      // step, ~1 ulp) per pivot gives both l = d * rsqrt(d) and 1/l: the pivot chain is the critical path
+      // of the whole factorisation, so sqrt-then-reciprocal (two long-latency sequences) is avoided.
+      float rl[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = a[j][j];
         if (!(d > 0.0f)) bad = true;
-        const float l = sqrtf(d);
-        const float rl = __frcp_rn(l);
-        a[j][j] = l;
+        float r = rsqrtf(d);
+        r = fmaf(r, fmaf(-0.5f * d * r, r, 0.5f), r);  // r += r * (0.5 - 0.5 * d * r^2)
+        rl[j] = r;
+        a[j][j] = d * r;
 #pragma unroll
-        for (int i = j + 1; i < 8; ++i) a[i][j] *= rl;
+        for (int i = j + 1; i < 8; ++i) a[i][j] *= r;
 #pragma unroll
         for (int c = j + 1; c < 8; ++c)
 #pragma unroll
@@ -124,14 +112,13 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, in
       for (int j = 0; j < 8; ++j) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) di[i][j] = 0.0f;
-        const float rj = __frcp_rn(a[j][j]);
-        di[j][j] = rj;
+        di[j][j] = rl[j];
 #pragma unroll
         for (int i = j + 1; i < 8; ++i) {
           float sacc = 0.f;
 #pragma unroll
           for (int m = j; m < i; ++m) sacc = fmaf(a[i][m], di[m][j], sacc);
-          di[i][j] = -sacc * __frcp_rn(a[i][i]);
+          di[i][j] = -sacc * rl[i];
         }
       }
 #pragma unroll
@@ -192,16 +179,12 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, in
     }
     // the next panel's P is written only after the next iteration's first barrier
   }
-  if (bad && status) atomicOr(status, LCB_ST_NOT_SPD);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int r = ty * 8 + i, cc = tx * 8 + c;
-      if (r < nb && cc < nb) A[(int64_t)r * ld + cc] = (cc <= r) ? a[i][c] : 0.0f;
-    }
-  __syncthreads();
+}
 
+// x = L^-1 for the factor held in `a` (dall from factor_block); x must enter as the identity tiles.
+// P: NB * PS floats, XP: 8 * (NB + 4) floats of scratch.
+__device__ __forceinline__ void invert_block(const float (&a)[8][8], float (&x)[8][8], float* P, float* XP,
+                                             float (*dall)[64], int ty, int tx) {
   // ================= X = L^-1, blocked forward substitution over the 16 row panels
 #pragma unroll 1
   for (int k = 0; k < 16; ++k) {
@@ -257,12 +240,228 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, in
     }
     __syncthreads();
   }
+}
+
+// One CTA: Cholesky of the nb x nb diagonal block at A (ld) in place and the inverse of the factor
+// (`dinv` [NB x NB], turns the panel TRSM into a GEMM).  Exact-fp32 path of lcb_chol_inv_upper.
+__global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, int nb, float* dinv, uint32_t* status) {
+  __shared__ float P[NB * PS];            // column panel  P[r][m] = L[r][p*8 + m]
+  __shared__ float XP[8 * (NB + 4)];      // row panel     XP[m][c] = X[k*8 + m][c]
+  __shared__ float dall[16][64];          // inverted diagonal tiles
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  float a[8][8], x[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      float v = (r == cc) ? 1.0f : 0.0f;  // identity padding for a short last block
+      if (r < nb && cc < nb) v = (cc <= r) ? A[(int64_t)r * ld + cc] : 0.0f;
+      a[i][c] = v;
+      x[i][c] = (r == cc) ? 1.0f : 0.0f;
+    }
+  bool bad = false;
+  factor_block(a, P, dall, bad, ty, tx);
+  if (bad && status) atomicOr(status, LCB_ST_NOT_SPD);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      if (r < nb && cc < nb) A[(int64_t)r * ld + cc] = (cc <= r) ? a[i][c] : 0.0f;
+    }
+  __syncthreads();
+  invert_block(a, x, P, XP, dall, ty, tx);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int r = ty * 8 + i, cc = tx * 8 + c;
       if (r < nb) dinv[r * NB + cc] = (cc <= r && cc < nb) ? x[i][c] : 0.0f;
+    }
+}
+
+// Tensor-core path, one launch per 128-column panel: every CTA factors the diagonal block itself
+// (redundantly -- the other SMs would idle otherwise, and it saves a launch plus a grid-wide dependency),
+// keeps L11 in shared memory and solves its own 128-row tile of the panel, L21 = A21 * L11^-T, with the same
+// 8-wide blocked steps (the 8 x 8 diagonal inverses come out of the factorisation).  The tile is written
+// back in place and as tf32 hi / lo planes (ld NB) for the SYRK GEMMs that follow.
+constexpr int LS = NB + 4;
+constexpr int PANEL_SMEM = (NB * LS + 2 * NB * PS + 16 * 64) * (int)sizeof(float);
+
+__global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, int64_t j, int nb, int64_t m2,
+                                                         float* Lblk, float* panelH, float* panelL, uint32_t* status) {
+  extern __shared__ __align__(16) float psm[];
+  float* Lsm = psm;                      // [NB][LS]  L11
+  float* P0 = Lsm + NB * LS;             // two column-panel buffers
+  float* P1 = P0 + NB * PS;
+  float(*dall)[64] = reinterpret_cast<float(*)[64]>(P1 + NB * PS);
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  float* Ajj = A + j * ld + j;
+  float a[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      float v = (r == cc) ? 1.0f : 0.0f;
+      if (r < nb && cc < nb) v = (cc <= r) ? Ajj[(int64_t)r * ld + cc] : 0.0f;
+      a[i][c] = v;
+    }
+  bool bad = false;
+  factor_block(a, P0, dall, bad, ty, tx);
+  if (blockIdx.x == 0) {
+    // L11 goes to a side buffer [NB x NB]: the other CTAs of this launch are still reading Ajj
+    if (bad && status) atomicOr(status, LCB_ST_NOT_SPD);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) Lblk[(ty * 8 + i) * NB + tx * 8 + c] = a[i][c];
+  }
+  if (m2 <= 0) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) Lsm[(ty * 8 + i) * LS + tx * 8 + c] = a[i][c];
+
+  // ---- my row tile of A21
+  const int64_t r0 = (int64_t)blockIdx.x * NB;  // first row of the tile inside the panel
+  float* A21 = A + (j + nb + r0) * ld + j;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool ok = r0 + ty * 8 + i < m2;
+    const float* rp = A21 + (int64_t)(ty * 8 + i) * ld + tx * 8;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (ok) { v0 = *reinterpret_cast<const float4*>(rp); v1 = *reinterpret_cast<const float4*>(rp + 4); }
+    a[i][0] = v0.x; a[i][1] = v0.y; a[i][2] = v0.z; a[i][3] = v0.w;
+    a[i][4] = v1.x; a[i][5] = v1.y; a[i][6] = v1.z; a[i][7] = v1.w;
+  }
+  __syncthreads();  // Lsm complete; factor_block's last use of P0 is over
+#pragma unroll 1
+  for (int p = 0; p < 16; ++p) {
+    float* P = (p & 1) ? P1 : P0;
+    if (tx == p) {  // X_ip = A_ip * L_pp^-T : new[i][c] = sum_{m <= c} a[i][m] * Dinv[c][m]
+      float dv[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dv[i][c] = dall[p][i * 8 + c];
+      float nw[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int m = 0; m <= c; ++m) acc = fmaf(a[i][m], dv[c][m], acc);
+          nw[i][c] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          a[i][c] = nw[i][c];
+          P[(ty * 8 + i) * PS + c] = nw[i][c];
+        }
+    }
+    __syncthreads();
+    if (tx > p) {  // A_i,tx -= X_ip * L_tx,p^T
+      float lr[8][8], lc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          lr[i][m] = P[(ty * 8 + i) * PS + m];
+          lc[i][m] = Lsm[(tx * 8 + i) * LS + p * 8 + m];
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float acc = a[i][c];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) acc = fmaf(-lr[i][m], lc[c][m], acc);
+          a[i][c] = acc;
+        }
+    }
+    // the other P buffer is written next: no barrier needed here (it was last read two steps ago,
+    // before the barrier above)
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t rl = r0 + ty * 8 + i;
+    if (rl >= m2) continue;
+    float* rp = A21 + (int64_t)(ty * 8 + i) * ld + tx * 8;
+    *reinterpret_cast<float4*>(rp) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
+    *reinterpret_cast<float4*>(rp + 4) = make_float4(a[i][4], a[i][5], a[i][6], a[i][7]);
+    float h[8], l[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a[i][c]));
+      h[c] = __uint_as_float(hb);
+      l[c] = __fsub_rn(a[i][c], h[c]);
+    }
+    float* hp = panelH + rl * NB + tx * 8;
+    float* lp = panelL + rl * NB + tx * 8;
+    *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(hp + 4) = make_float4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<float4*>(lp + 4) = make_float4(l[4], l[5], l[6], l[7]);
+  }
+}
+
+// Inverse of every 128 x 128 diagonal block of the factor, in place (base of the trtri recursion): one CTA
+// per block, all blocks in one launch.
+__global__ void __launch_bounds__(256) diag_inv_kernel(float* A, int64_t k, const float* Lblk_all) {
+  __shared__ float P[NB * PS];
+  __shared__ float XP[8 * (NB + 4)];
+  __shared__ float dall[16][64];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int64_t j = (int64_t)blockIdx.x * NB;
+  const int nb = (int)min((int64_t)NB, k - j);
+  float* Ajj = A + j * k + j;
+  const float* Lb = Lblk_all + (int64_t)blockIdx.x * NB * NB;  // factor block (identity padded) from chol_panel_kernel
+  float a[8][8], x[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      a[i][c] = Lb[r * NB + cc];
+      x[i][c] = (r == cc) ? 1.0f : 0.0f;
+    }
+  if (ty == tx) {  // inverse of my 8 x 8 diagonal tile of L
+    float di[8][8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) di[i][jj] = 0.0f;
+      di[jj][jj] = __frcp_rn(a[jj][jj]);
+#pragma unroll
+      for (int i = jj + 1; i < 8; ++i) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int m = jj; m < i; ++m) sacc = fmaf(a[i][m], di[m][jj], sacc);
+        di[i][jj] = -sacc * __frcp_rn(a[i][i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dall[ty][i * 8 + c] = di[i][c];
+  }
+  __syncthreads();
+  invert_block(a, x, P, XP, dall, ty, tx);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int r = ty * 8 + i, cc = tx * 8 + c;
+      if (r < nb && cc < nb) Ajj[(int64_t)r * k + cc] = (cc <= r) ? x[i][c] : 0.0f;
     }
 }
 
@@ -278,6 +477,37 @@ __global__ void put_diag_blocks_kernel(float* A, int64_t k, const float* dinv_al
 
 }  // namespace
 
+// Two side streams + events per host thread and device for the look-ahead of the tensor-core Cholesky.
+struct SideStreams {
+  cudaStream_t s[2];
+  cudaEvent_t evP, evB[2], evS[2];
+};
+static SideStreams* side_streams() {
+  static thread_local SideStreams cache[16];
+  static thread_local bool ready[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) {
+    set_error("side_streams: cudaGetDevice failed or device index >= 16");
+    return nullptr;
+  }
+  if (!ready[dev]) {
+    SideStreams& c = cache[dev];
+    bool ok = true;
+    for (int i = 0; i < 2; ++i) ok = ok && cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c.evP, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2; ++i) {
+      ok = ok && cudaEventCreateWithFlags(&c.evB[i], cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&c.evS[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+      set_error("side_streams: cannot create CUDA streams / events");
+      return nullptr;
+    }
+    ready[dev] = true;
+  }
+  return &cache[dev];
+}
+
 constexpr int SW = 512;        // super-panel width of the tensor-core path (Kd of the big SYRK)
 constexpr int TRI_TG_MIN = 1024;  // trtri levels with node size >= this run on the tensor cores
 constexpr int TG_CHAIN = 256;     // accumulation chain length (columns) of the tensor-core contractions
@@ -290,8 +520,8 @@ static size_t chol_ws_floats(int64_t k) {
   return (size_t)(k * k)                 // work matrix
          + std::max(t_exact, t_tg)       // T of the trtri recursion / operand planes
          + (size_t)(nblk * NB * NB)      // inverted diagonal blocks
-         + (size_t)(3 * kp * NB)         // TRSM panel + its hi / lo planes
-         + (size_t)(2 * kp * SW)         // hi / lo planes of a super-panel strip
+         + (size_t)(4 * kp * NB)         // TRSM panel (exact path) / two sets of panel hi + lo planes
+         + (size_t)(4 * kp * SW)         // two sets of hi / lo planes of a super-panel strip
          + 64;
 }
 
@@ -322,13 +552,11 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   float* T = A + k * k;
   const size_t t_floats = std::max((size_t)(k * k / 2 + k * NB), (size_t)(9 * (kp / 2 + NB) * (kp / 2 + NB)));
   float* dinv_all = T + t_floats;
-  float* panel = dinv_all + nblk * NB * NB;
-  float* panelH = panel + kp * NB;
-  float* panelL = panelH + kp * NB;
-  float* stripH = panelL + kp * NB;
-  float* stripL = stripH + kp * SW;
-  float* dsum = stripL + kp * SW;
+  float* panel = dinv_all + nblk * NB * NB;   // exact path: [k, NB]; tensor-core path: planes [set][hi|lo][kp, NB]
+  float* strip = panel + 4 * kp * NB;         // planes [set][hi|lo][kp, SW]
+  float* dsum = strip + 4 * kp * SW;
   const bool tg = gemm_mode() == 1 && k % 4 == 0 && tg_ok(ws, 4) && k > NB;
+  if (tg) LCB_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
 
   diag_sum_kernel<<<1, 1024, 0, st>>>(H, k, dsum);
   LCB_LAUNCH_CHECK();
@@ -360,44 +588,96 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
       if (rc != LCB_OK) return rc;
     }
   } else {
-    // ---- tensor-core path: two-level right-looking Cholesky.  Inside a super-panel of SW columns the
-    // 128-wide panel updates touch only the rest of the super-panel strip (Kd = 128, small N); the
-    // trailing matrix beyond the strip gets one SYRK with Kd = SW per super-panel.
-    for (int64_t j0 = 0; j0 < k; j0 += SW) {
+    // ---- tensor-core path: two-level right-looking Cholesky with look-ahead.
+    // Inside a super-panel of SW columns the 128-wide panel updates touch only the rest of the super-panel
+    // strip (Kd = 128); the trailing matrix beyond the strip gets one SYRK with Kd = SW per super-panel.
+    // The panel kernels are a latency-bound chain, so every update is split in two: the part the NEXT
+    // panel / super-panel needs (one column block / one strip) stays on the caller's stream, the rest runs
+    // on a side stream underneath the following panel kernels.  All updates are L2 reduce-adds, so they
+    // commute; events order them against the readers, and the hi / lo planes are double-buffered.
+    SideStreams* ss = side_streams();
+    if (ss == nullptr) return LCB_ERR_CUDA;
+    auto fail = [&](int code) {  // nothing may outlive the workspace
+      cudaStreamSynchronize(ss->s[0]);
+      cudaStreamSynchronize(ss->s[1]);
+      return code;
+    };
+    int64_t q = 0;  // panel counter
+    bool evB_live[2] = {false, false}, evS_live[2] = {false, false};
+    int64_t J = 0;
+    for (int64_t j0 = 0; j0 < k; j0 += SW, ++J) {
       const int64_t j1 = std::min<int64_t>(j0 + SW, k);
-      for (int64_t j = j0; j < j1; j += NB) {
+      // strip J was updated by S_A(J-1) (this stream) and S_B(J-2) (side stream 1); S_B(J-2) also used the
+      // strip planes of parity J & 1 that this super-panel will overwrite
+      if (evS_live[J & 1]) { LCB_CUDA(cudaStreamWaitEvent(st, ss->evS[J & 1], 0)); evS_live[J & 1] = false; }
+      for (int64_t j = j0; j < j1; j += NB, ++q) {
         const int nb = (int)std::min<int64_t>(NB, k - j);
-        float* Ajj = A + j * k + j;
-        float* dinv = dinv_all + (j / NB) * NB * NB;
-        potf2_inv_kernel<<<1, 256, 0, st>>>(Ajj, k, nb, dinv, status);
-        LCB_LAUNCH_CHECK();
         const int64_t m2 = k - j - nb;
+        float* pH = panel + (q & 1) * 2 * kp * NB;
+        float* pL = pH + kp * NB;
+        // column block j was updated by A(q-1) (this stream) and B(q-2) (side stream 0), which also read the
+        // panel planes of parity q & 1
+        if (evB_live[q & 1]) { LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[q & 1], 0)); evB_live[q & 1] = false; }
+        // potf2 of the diagonal block + TRSM of the panel rows + tf32 split, one launch
+        const unsigned ctas = m2 > 0 ? (unsigned)ceil_div(m2, NB) : 1u;
+        chol_panel_kernel<<<ctas, 256, PANEL_SMEM, st>>>(A, k, j, nb, m2, dinv_all + (j / NB) * NB * NB, pH, pL, status);
+        LCB_LAUNCH_CHECK();
         if (m2 <= 0) break;
-        float* A21 = A + (j + nb) * k + j;
-        // L21 = A21 * L11^-T in place (a CTA reads its 128 rows completely before it writes them)
-        rc = sgemm(gemm_args(A21, k, dinv, NB, A21, k, (int)m2, nb, nb, 1.0f, 0.0f, /*transB=*/1), st);
-        if (rc != LCB_OK) return rc;
         const int64_t nrest = j1 - (j + nb);  // columns of the strip still to be updated
         if (nrest > 0) {
-          if ((rc = split_tf32(A21, k, (int)m2, nb, panelH, panelL, NB, 0, st)) != LCB_OK) return rc;
-          rc = tgemm_nt(panelH, panelL, NB, panelH, panelL, NB, A + (j + nb) * k + (j + nb), k, (int)m2, (int)nrest, nb,
-                        -1.0f, TG_LOWER_OUT, st);
-          if (rc != LCB_OK) return rc;
+          const int64_t nB = nrest - nb;       // columns beyond the next block
+          if (nB > 0) {                        // B(q): rows / columns from j + 2 nb on, side stream 0
+            LCB_CUDA(cudaEventRecord(ss->evP, st));
+            LCB_CUDA(cudaStreamWaitEvent(ss->s[0], ss->evP, 0));
+            rc = tgemm_nt(pH + nb * NB, pL + nb * NB, NB, pH + nb * NB, pL + nb * NB, NB,
+                          A + (j + 2 * nb) * k + (j + 2 * nb), k, (int)(m2 - nb), (int)nB, nb, -1.0f, TG_LOWER_OUT, ss->s[0]);
+            if (rc != LCB_OK) return fail(rc);
+            LCB_CUDA(cudaEventRecord(ss->evB[q & 1], ss->s[0]));
+            evB_live[q & 1] = true;
+          }
+          // A(q): the next column block, this stream
+          rc = tgemm_nt(pH, pL, NB, pH, pL, NB, A + (j + nb) * k + (j + nb), k, (int)m2, (int)std::min<int64_t>(nb, nrest),
+                        nb, -1.0f, TG_LOWER_OUT, st);
+          if (rc != LCB_OK) return fail(rc);
         }
       }
       const int64_t m3 = k - j1;
       if (m3 > 0) {
+        // the strip is final once the last B of this super-panel is done
+        for (int e = 0; e < 2; ++e)
+          if (evB_live[e]) { LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[e], 0)); evB_live[e] = false; }
         const int kd = (int)(j1 - j0);
-        if ((rc = split_tf32(A + j1 * k + j0, k, (int)m3, kd, stripH, stripL, SW, 0, st)) != LCB_OK) return rc;
-        rc = tgemm_nt(stripH, stripL, SW, stripH, stripL, SW, A + j1 * k + j1, k, (int)m3, (int)m3, kd, -1.0f,
+        float* sH = strip + (J & 1) * 2 * kp * SW;
+        float* sL = sH + kp * SW;
+        if ((rc = split_tf32(A + j1 * k + j0, k, (int)m3, kd, sH, sL, SW, 0, st)) != LCB_OK) return fail(rc);
+        const int64_t nS = m3 - SW;  // rows / columns beyond the next strip
+        if (nS > 0) {                // S_B(J), side stream 1
+          LCB_CUDA(cudaEventRecord(ss->evP, st));
+          LCB_CUDA(cudaStreamWaitEvent(ss->s[1], ss->evP, 0));
+          rc = tgemm_nt(sH + SW * SW, sL + SW * SW, SW, sH + SW * SW, sL + SW * SW, SW, A + (j1 + SW) * k + (j1 + SW), k,
+                        (int)nS, (int)nS, kd, -1.0f, TG_LOWER_OUT, ss->s[1], TG_CHAIN);
+          if (rc != LCB_OK) return fail(rc);
+          LCB_CUDA(cudaEventRecord(ss->evS[J & 1], ss->s[1]));
+          evS_live[J & 1] = true;
+        }
+        // S_A(J): the next strip, this stream
+        rc = tgemm_nt(sH, sL, SW, sH, sL, SW, A + j1 * k + j1, k, (int)m3, (int)std::min<int64_t>(SW, m3), kd, -1.0f,
                       TG_LOWER_OUT, st, TG_CHAIN);
-        if (rc != LCB_OK) return rc;
+        if (rc != LCB_OK) return fail(rc);
       }
+    }
+    for (int e = 0; e < 2; ++e) {
+      if (evB_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[e], 0));
+      if (evS_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evS[e], 0));
     }
   }
   zero_strict_upper_kernel<<<g2, 256, 0, st>>>(A, k);
   LCB_LAUNCH_CHECK();
-  put_diag_blocks_kernel<<<(unsigned)nblk, 256, 0, st>>>(A, k, dinv_all);
+  if (tg) {
+    diag_inv_kernel<<<(unsigned)nblk, 256, 0, st>>>(A, k, dinv_all);  // all diagonal blocks inverted in one launch
+  } else {
+    put_diag_blocks_kernel<<<(unsigned)nblk, 256, 0, st>>>(A, k, dinv_all);
+  }
   LCB_LAUNCH_CHECK();
 
   // ---- recursive triangular inverse, in place: [[A,0],[C,B]]^-1 = [[A^-1,0],[-B^-1 C A^-1, B^-1]]
