@@ -188,9 +188,12 @@ def run_ours(args):
             self.weight = torch.nn.Parameter(w, requires_grad=False)
             self.weight_quantizer = lc.FakeQuantizer.build(WCFG).to(dev)
 
+    stage_evs = []  # (hessian end, factorize end, update end) events of the last step
+
     def one_model(from_host):
         """One step. Returns the (start, end, flops) CUDA events of every Hessian accumulation."""
         evs = []
+        stage_evs.clear()
         cur = torch.cuda.current_stream(dev)
         staged = {}
 
@@ -219,7 +222,9 @@ def run_ours(args):
                 ops.hessian_finalize(H, 2.0 / n, True)
                 e1.record()
                 evs.append((e0, e1, 2.0 * SEQ_LEN * K * K * len(my_samples), K))
+                e2 = torch.cuda.Event(enable_timing=True)
                 fac = solvers.factorize(H, WCFG["group_size"], actorder=True, percdamp=0.01)
+                e2.record()
                 del H
                 if from_host:
                     w, ev = staged.pop((layer, gi))
@@ -233,7 +238,10 @@ def run_ours(args):
                 # for separate modules; here the weights are stored stacked)
                 lin = Lin(w[rows])
                 solvers.update_weight(lin, dev, block_size=128, percdamp=0.01, actorder=True, factor=fac)
+                e3 = torch.cuda.Event(enable_timing=True)
+                e3.record()
                 out = parallel.gather_rows(lin.weight.data, ntot)
+                stage_evs.append((e1, e2, e3))
                 if from_host:  # device -> pinned host buffer, asynchronous
                     out_host[layer][gi].copy_(out, non_blocking=True)
         return evs
@@ -269,6 +277,9 @@ def run_ours(args):
     hess_flops = sum(f for _, _, f, _ in evs)
     hess_exec = sum(f * hessian_executed_fraction(K) for _, _, f, K in evs)
     hess_ms_total = sum(a.elapsed_time(b) for a, b, _, _ in evs)
+    fact_ms = sum(a.elapsed_time(b) for a, b, _ in stage_evs)      # last step (rank 0's view)
+    upd_ms = sum(b.elapsed_time(c) for _, b, c in stage_evs)
+    hess_last_ms = sum(a.elapsed_time(b) for a, b, _, _ in evs[-len(stage_evs):]) if stage_evs else 0.0
     n_hess_launch = len(evs) * len(my_samples)
 
     e2e_steps = max(1, min(args.steps, 2))
@@ -308,6 +319,11 @@ def run_ours(args):
                         "copied back to pinned host memory; activations are produced on the device in the "
                         "reference flow too"},
         "gpu_launches": int(launches),
+        "stages_s_per_model": {"hessian (incl. all-reduce + finalize)": hess_last_ms / 1e3,
+                               "factorize (dead fix, act-order sort, Cholesky-inverse)": fact_ms / 1e3,
+                               "update (find_params, permutes, block loop, lazy-batch GEMMs)": upd_ms / 1e3,
+                               "note": "device time between CUDA events of the last timed step; the rest of `value` is "
+                                       "the row all-gather (N > 1) and allocator / launch gaps"},
         "clocks": clocks,
         "roofline": {"kernel": "hessian_umma_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,

@@ -64,7 +64,9 @@ typedef struct lcb_quant_cfg {
   int32_t elem;        /* LCB_E_* */
   int32_t zero_point;  /* asymmetric */
   int32_t scale_ebits; /* MX shared-exponent bits (ref: mx_quant.py:63), 8 */
-  int32_t reserved[4];
+  int32_t mse;         /* find_params with the clip search (ref: int_quant.py:115-162): 80 shrink steps, |.|^2.4 error;
+                          INT / FP / MX, axis -1, cols % group == 0; else LCB_ERR_UNSUPPORTED */
+  int32_t reserved[3];
 } lcb_quant_cfg;
 
 /* mode bits of lcb_qdq */

@@ -35,7 +35,8 @@ class QuantCfg(ctypes.Structure):
         ("elem", ctypes.c_int32),
         ("zero_point", ctypes.c_int32),
         ("scale_ebits", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 4),
+        ("mse", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 3),
     ]
 
 
@@ -152,7 +153,8 @@ def check(rc, what):
         raise LcbError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else ""))
 
 
-def make_cfg(qtype, elem, zero_point, scale_ebits=8):
+def make_cfg(qtype, elem, zero_point, scale_ebits=8, mse=False):
     c = QuantCfg()
     c.qtype, c.elem, c.zero_point, c.scale_ebits = int(qtype), int(elem), int(bool(zero_point)), int(scale_ebits)
+    c.mse = int(bool(mse))
     return c

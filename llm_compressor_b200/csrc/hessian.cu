@@ -25,7 +25,25 @@
 
 #include "umma.cuh"
 
+#include <atomic>
+#include <cstdlib>
+
 namespace lcb {
+
+// Which tcgen05 kernel accumulates X^T X: one CTA per 128 x 256 tile (cta_group::1) or CTA pairs on 256 x 256
+// tiles (cta_group::2).  Measured on B200 (2048 tokens, symmetric half): k = 8192 pair 0.117 ms vs 0.129 ms,
+// k = 3072 pair 0.031 ms vs 0.029 ms (fewer, larger work units and two cluster barriers per launch), so the
+// pair kernel is used from k = 4096 up.  LCB_HESSIAN_PAIR = 0 / 1 forces one of them (A/B measurements).
+static std::atomic<int> g_hessian_pair{-2};
+static bool hessian_pair_mode(int64_t k) {
+  int m = g_hessian_pair.load(std::memory_order_relaxed);
+  if (m == -2) {
+    const char* e = std::getenv("LCB_HESSIAN_PAIR");
+    m = e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
+    g_hessian_pair.store(m, std::memory_order_relaxed);
+  }
+  return m < 0 ? k >= 4096 : m != 0;
+}
 
 namespace {
 
@@ -79,15 +97,15 @@ struct HessArgs {
   int16_t row_start[MAX_TILES_M + 1];  // prefix sum of computed tiles per tile row
 };
 
-// linear computed-tile index -> (m0, n0)
-__device__ __forceinline__ void tile_coords(const HessArgs& a, int tile, int& m0, int& n0) {
+// linear computed-tile index -> (m0, n0) for bm x BN tiles
+__device__ __forceinline__ void tile_coords(const HessArgs& a, int tile, int& m0, int& n0, int bm = BM) {
   int lo = 0, hi = a.tiles_m;  // largest mt with row_start[mt] <= tile
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (a.row_start[mid] <= tile) lo = mid; else hi = mid;
   }
-  const int first_nt = a.upper_only ? (lo * BM) / BN : 0;
-  m0 = lo * BM;
+  const int first_nt = a.upper_only ? (lo * bm) / BN : 0;
+  m0 = lo * bm;
   n0 = (first_nt + (tile - a.row_start[lo])) * BN;
 }
 
@@ -250,6 +268,187 @@ hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2): two CTAs of a cluster compute one 256 x 256 tile of H.  Each CTA stages
+// its own 128 rows of A and HALF of B (128 channels) -- 32 KB per 64-token stage instead of 48 KB -- and the
+// leader issues tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared memory; each CTA ends up
+// with its 128 x 256 half of the accumulator in its own TMEM and runs its own epilogue.  ncu on the
+// single-CTA kernel: tensor pipe 48 % active, bounded by operand traffic into / out of shared memory
+// (12 KB read per 128-cycle MMA + 48 KB of TMA writes per 512 cycles against 128 B/clk); the pair halves
+// the B traffic per SM, which is what cuBLAS' 2-SM kernels do to reach the measured 1.4-1.6 PFLOP/s.
+constexpr int PM = 128;                                   // rows of the tile per CTA
+constexpr int P_STAGES = 6;
+constexpr int PA_BYTES = (PM / BOX_C) * BOX_BYTES;        // 16384
+constexpr int PB_BYTES = (BN / 2 / BOX_C) * BOX_BYTES;    // 16384: this CTA's half of B
+constexpr int P_STAGE_BYTES = PA_BYTES + PB_BYTES;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + OUT_BYTES + 256 + 1024;
+
+constexpr uint32_t make_idesc_pair() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)((2 * PM) >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+hessian_umma_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_h, const __grid_constant__ HessArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + P_STAGES * PA_BYTES;
+  uint8_t* smem_out = smem + P_STAGES * P_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + OUT_BYTES);
+  uint64_t* full = bars;                         // [P_STAGES]  TMA (both CTAs) -> MMA; the leader's copy is used
+  uint64_t* empty = bars + P_STAGES;             // [P_STAGES]  MMA -> TMA, signalled in both CTAs
+  uint64_t* tfull = bars + 2 * P_STAGES;         // [2]         MMA -> epilogue, signalled in both CTAs
+  uint64_t* tempty = bars + 2 * P_STAGES + 2;    // [2]         epilogues of both CTAs -> MMA; the leader's copy is used
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int64_t units = (int64_t)a.num_tiles * a.kblocks;
+  const int64_t u0 = units * cluster / nclusters, u1 = units * (cluster + 1) / nclusters;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_h)) : "memory");
+    for (int i = 0; i < P_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): my 128 rows of A, my 128 channels of B
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = u0; u < u1;) {
+        const int tile = (int)(u / a.kblocks);
+        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
+        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+        int m0, n0;
+        tile_coords(a, tile, m0, n0, 2 * PM);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * P_STAGE_BYTES);  // both CTAs' boxes land on the leader's barrier
+          const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+          uint8_t* sa = smem_a + stage * PA_BYTES;
+          uint8_t* sb = smem_b + stage * PB_BYTES;
+#pragma unroll
+          for (int h = 0; h < PM / BOX_C; ++h)
+            tma_load_2d_pair(&map_a, lead_full, sa + h * BOX_BYTES, m0 + (int)rank * PM + h * BOX_C, kb * BKT);
+#pragma unroll
+          for (int h = 0; h < BN / 2 / BOX_C; ++h)
+            tma_load_2d_pair(&map_b, lead_full, sb + h * BOX_BYTES, n0 + (int)rank * (BN / 2) + h * BOX_C, kb * BKT);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+        u += kb1 - kb0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA only
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_pair();
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int64_t u = u0; u < u1; ++iter) {
+        const int tile = (int)(u / a.kblocks);
+        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
+        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t sa = smem_u32(smem_a + stage * PA_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * PB_BYTES);
+#pragma unroll
+          for (int k = 0; k < BKT / UMMA_K; ++k) {
+            const uint64_t da = make_desc(sa + k * UMMA_K * 128);
+            const uint64_t db = make_desc(sb + k * UMMA_K * 128);
+            umma_bf16_pair(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty[stage], 3);  // frees the slot in both CTAs
+          if (kb == kb1 - 1) umma_commit_pair(&tfull[as], 3);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+        u += kb1 - kb0;
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): my 128 x 256 half of the tile
+    const int q = warp & 3;
+    uint8_t* obuf = smem_out + (warp - 2) * 2 * OUT_BUF_BYTES;
+    int iter = 0, nstore = 0;
+    for (int64_t u = u0; u < u1; ++iter) {
+      const int tile = (int)(u / a.kblocks);
+      const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
+      const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      int m0, n0;
+      tile_coords(a, tile, m0, n0, 2 * PM);
+      mbar_wait(&tfull[as], aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const int row0 = m0 + (int)rank * PM + q * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        const bool live = row0 < a.k && col0 < a.k && !(a.upper_only && col0 + 31 < row0);
+        if (!live) continue;  // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
+        uint8_t* buf = obuf + (nstore & 1) * OUT_BUF_BYTES;
+        if (nstore >= 2) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 o = make_float4(a.alpha * v[4 * j], a.alpha * v[4 * j + 1], a.alpha * v[4 * j + 2],
+                                       a.alpha * v[4 * j + 3]);
+          *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&map_h, buf, col0, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++nstore;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));  // the leader's MMA warp waits for 8 warps
+      u += kb1 - kb0;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  // nobody leaves while the partner may still signal its barriers or read its shared memory
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
 // dX split for GPTAQ: d = X_fp - X (exact in fp32 for bf16 inputs of similar magnitude),
 // hi = bf16(d), lo = bf16(d - hi)  ->  d^T X = hi^T X + lo^T X with ~16 mantissa bits of d.
 __global__ void dx_split_kernel(const __nv_bfloat16* __restrict__ xfp, const __nv_bfloat16* __restrict__ x,
@@ -373,7 +572,9 @@ int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens,
   if (rc != LCB_OK) return rc;
   HessArgs a{};
   a.k = k; a.tokens = tokens; a.alpha = alpha; a.upper_only = upper_only;
-  a.tiles_m = (int)ceil_div(k, BM); a.tiles_n = (int)ceil_div(k, BN);
+  const bool pair = hessian_pair_mode(k);
+  const int bm = pair ? 2 * PM : BM;
+  a.tiles_m = (int)ceil_div(k, bm); a.tiles_n = (int)ceil_div(k, BN);
   if (a.tiles_m > MAX_TILES_M) {
     set_error("lcb_hessian_accum: k = %lld is larger than the supported 16384", (long long)k);
     return LCB_ERR_UNSUPPORTED;
@@ -381,14 +582,34 @@ int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens,
   int acc = 0;
   for (int mt = 0; mt < a.tiles_m; ++mt) {
     a.row_start[mt] = (int16_t)acc;
-    const int first_nt = upper_only ? (mt * BM) / BN : 0;
-    acc += a.tiles_n - first_nt;
+    const int first_nt = upper_only ? (mt * bm) / BN : 0;
+    acc += a.tiles_n > first_nt ? a.tiles_n - first_nt : 0;
   }
   a.row_start[a.tiles_m] = (int16_t)acc;
   a.num_tiles = acc;
   a.kblocks = (int)ceil_div(tokens, BKT);
-  LCB_CUDA(cudaFuncSetAttribute(hessian_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int64_t units = (int64_t)a.num_tiles * a.kblocks;
+  if (pair) {
+    LCB_CUDA(cudaFuncSetAttribute(hessian_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    // one CTA pair per TPC; never less than ~4 token blocks per pair
+    int clusters = sm_count() / 2;
+    const int64_t cap = units / 4 > 0 ? units / 4 : 1;
+    if (clusters > cap) clusters = (int)cap;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = P_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    LCB_CUDA(cudaLaunchKernelEx(&cfg, hessian_umma_pair_kernel, map_a, map_b, map_h, a));
+    return LCB_OK;
+  }
+  LCB_CUDA(cudaFuncSetAttribute(hessian_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   // one CTA per SM; never less than ~8 token blocks per CTA so the epilogue stays amortised
   int grid = sm_count();
   const int64_t cap = units / 8 > 0 ? units / 8 : 1;

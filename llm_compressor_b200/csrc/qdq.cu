@@ -26,6 +26,7 @@ struct QdqArgs {
   int64_t group;
   int64_t G;  // groups per row (axis -1) / per column (axis -2)
   int find, apply;
+  int mse;  // find_params with the mse clip search
   QCfg c;
 };
 
@@ -486,6 +487,69 @@ __global__ void __launch_bounds__(256) qdq_generic_kernel(QdqArgs a, uint32_t* a
 }
 
 // ------------------------------------------------------------------------------------------
+// mse clip search (ref: int_quant.py:115-162, fp_quant.py:127-174, mx_quant.py:114-149): 80 shrink factors
+// p = 1 - i/100 of the group's (max, min); candidate parameters from the shrunken range (scale NOT clamped),
+// error sum_i |QDQ(x_i) - x_i|^2.4 with every op rounded in the tensor dtype, the sum accumulated in fp32 and
+// rounded once; the first candidate with a strictly smaller error wins.  One warp per group; the group is
+// re-read from L1 for every candidate (the reference makes 80 passes over HBM with ~25 kernels each).
+template <typename T>
+__global__ void __launch_bounds__(256) qdq_mse_kernel(QdqArgs a) {
+  constexpr int DT = DtOf<T>::value;
+  const T* x = static_cast<const T*>(a.x);
+  T* sc = static_cast<T*>(a.scales);
+  T* zr = static_cast<T*>(a.zeros);
+  const int lane = threadIdx.x & 31;
+  const int64_t total = a.nrows * a.G;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float nv_g = (a.c.qtype == LCB_Q_NVFP) ? *a.nv_amax : 0.0f;
+  for (int64_t gid = warp; gid < total; gid += nwarps) {
+    const T* xp = x + gid * a.group;  // groups tile the rows
+    float mx = -INFINITY, mn = INFINITY, amax = 0.0f;
+    for (int64_t i = lane; i < a.group; i += 32) {
+      const float v = to_f<T>(xp[i]);
+      mx = nan_max(mx, v); mn = nan_min(mn, v); amax = nan_max(amax, fabsf(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      amax = nan_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    if (!a.c.zero_point) { mx = amax; mn = -amax; }  // max_val = |x|.amax(), min_val = -max_val
+    float s_sel, z_sel, best = INFINITY;
+    find_params_unclamped<DT>(a.c, mx, mn, amax, nv_g, s_sel, z_sel);
+#pragma unroll 1
+    for (int it = 0; it < 80; ++it) {
+      const float p = (float)(1.0 - (double)it / 100.0);
+      const float mx1 = R<DT>(__fmul_rn(mx, p)), mn1 = R<DT>(__fmul_rn(mn, p));
+      float s1, z1;
+      // NVFP: the tensor-wide amax of the shrunken block maxima is p * g (monotone rounding), nvfp_quant.py:121-131
+      find_params_unclamped<DT>(a.c, mx1, mn1, mx1, R<DT>(__fmul_rn(nv_g, p)), s1, z1);
+      float acc = 0.0f;
+      for (int64_t i = lane; i < a.group; i += 32) {
+        const float v = to_f<T>(xp[i]);
+        float code;
+        const float dq = fake_quant<DT>(a.c, v, s1, z1, code);
+        const float d = fabsf(R<DT>(__fsub_rn(dq, v)));
+        // pow_(2.4): torch casts the python exponent to the tensor dtype first (bf16(2.4) = 2.40625)
+        acc = __fadd_rn(acc, R<DT>(powf(d, R<DT>(2.4f))));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+      const float err = R<DT>(acc);
+      if (err < best) { best = err; s_sel = s1; z_sel = z1; }
+    }
+    if (lane == 0) {
+      const float s = clamp_min_nan(s_sel, scale_floor<DT>());
+      flag_nan_scale(a, s);
+      sc[gid] = from_f<T>(s);
+      zr[gid] = from_f<T>(z_sel);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // axis -2 (groups run down the rows, one parameter per column): statistics kernel + apply kernel.
 // stats: CTA = (32 x 8) threads over a [group rows x 64 columns] tile; thread (tx, ty) owns
 // columns 2*tx, 2*tx+1 and rows ty, ty+8, ...  Coalesced 128 B row segments for bf16.
@@ -865,6 +929,14 @@ static int qdq_typed(QdqArgs a, int axis, int64_t batch, void* ws, size_t ws_byt
       if (rc != LCB_OK) return rc;
       a.nv_amax = reinterpret_cast<const float*>(keys);
     }
+    if (a.find && a.mse) {
+      // clip search writes the parameters, the ordinary kernels apply them
+      const int64_t total = a.nrows * a.G;
+      qdq_mse_kernel<T><<<grid_for(total, 8, 8), 256, 0, st>>>(a);
+      LCB_LAUNCH_CHECK();
+      if (!a.apply) return LCB_OK;
+      a.find = 0;
+    }
     return launch_rowwise<T, false>(a, nullptr, st);
   }
   // axis == -2
@@ -952,6 +1024,14 @@ extern "C" int lcb_qdq(const lcb_quant_cfg* cfg, int dtype, int mode, const void
   a.nv_amax = nv_amax; a.status = status;
   a.cols = cols; a.group = group; a.find = find; a.apply = apply;
   a.c = make_qcfg(cfg);
+  a.mse = (find && cfg->mse) ? 1 : 0;
+  if (a.mse) {
+    if ((cfg->qtype == LCB_Q_NVFP && cfg->zero_point) || axis != -1 || group <= 0 || cols % group != 0) {
+      set_error("lcb_qdq: the mse clip search is implemented for INT / FP / MX / symmetric NVFP, axis -1, groups tiling the rows");
+      return LCB_ERR_UNSUPPORTED;
+    }
+    LCB_REQUIRE(scales != nullptr && zeros != nullptr, "lcb_qdq: mse needs scales / zeros output buffers");
+  }
   if (group == 0 || axis == -1) {
     a.nrows = batch * rows; a.rows = rows;
     a.G = group ? ceil_div(cols, group) : 1;

@@ -84,31 +84,35 @@ __device__ __forceinline__ float elem_core(float A, const Fmt& f) {
 // torch promotes `0-dim bf16 (op) 0-dim fp32 buffer` to fp32.
 
 // int_quant.py:90-112,164
-template <int DT, int PDT>
+// CLAMP = false: the scale before clamp(min=1e-5), as the mse clip search uses it (int_quant.py:129-135)
+template <int DT, int PDT, bool CLAMP = true>
 __device__ __forceinline__ void int_params(float mx, float mn, float amax, int zp, const Fmt& f, float& s, float& z) {
   if (zp) {
     float range = R<DT>(__fsub_rn(mx, mn));
     float s0 = R<PDT>(__fdiv_rn(range, __fsub_rn(f.qmax, -f.qmax)));
     float t = R<PDT>(__fdiv_rn(mn, s0));
     z = rintf(R<PDT>(__fsub_rn(-f.qmax, t)));
-    s = clamp_min_nan(s0, scale_floor<PDT>());
+    s = CLAMP ? clamp_min_nan(s0, scale_floor<PDT>()) : s0;
   } else {
-    s = clamp_min_nan(R<PDT>(__fdiv_rn(amax, f.qmax)), scale_floor<PDT>());
+    const float s0 = R<PDT>(__fdiv_rn(amax, f.qmax));
+    s = CLAMP ? clamp_min_nan(s0, scale_floor<PDT>()) : s0;
     z = 0.0f;
   }
 }
 
 // fp_quant.py:102-124,176
-template <int DT, int PDT>
+template <int DT, int PDT, bool CLAMP = true>
 __device__ __forceinline__ void fp_params(float mx, float mn, float amax, int zp, const Fmt& f, float& s, float& z) {
+  float s0;
   if (zp) {
     float range = R<DT>(__fsub_rn(mx, mn));
-    s = clamp_min_nan(R<PDT>(__fdiv_rn(range, __fmul_rn(2.0f, f.max_norm))), scale_floor<PDT>());
+    s0 = R<PDT>(__fdiv_rn(range, __fmul_rn(2.0f, f.max_norm)));
     z = R<DT>(__fmul_rn(R<DT>(__fadd_rn(mx, mn)), 0.5f));
   } else {
-    s = clamp_min_nan(R<PDT>(__fdiv_rn(amax, f.max_norm)), scale_floor<PDT>());
+    s0 = R<PDT>(__fdiv_rn(amax, f.max_norm));
     z = 0.0f;
   }
+  s = CLAMP ? clamp_min_nan(s0, scale_floor<PDT>()) : s0;
 }
 
 // mx_quant.py:88-101: 2^clamp(floor(log2(v)) - emax_elem).  log2 is evaluated in the tensor
@@ -124,7 +128,7 @@ __device__ __forceinline__ float mx_shared_scale(float v, const QCfg& c) {
   return R<DT>(exp2f(se));  // integer argument: exact (2^128 -> inf, 2^-127 -> denormal)
 }
 
-template <int DT>
+template <int DT, bool CLAMP = true>
 __device__ __forceinline__ void mx_params(float mx, float mn, float amax, const QCfg& c, float& s, float& z) {
   float v = amax;
   z = 0.0f;
@@ -132,7 +136,8 @@ __device__ __forceinline__ void mx_params(float mx, float mn, float amax, const 
     z = R<DT>(__fmul_rn(R<DT>(__fadd_rn(mx, mn)), 0.5f));
     v = R<DT>(__fsub_rn(mx, z));
   }
-  s = clamp_min_nan(mx_shared_scale<DT>(v, c), scale_floor<DT>());
+  const float s0 = mx_shared_scale<DT>(v, c);
+  s = CLAMP ? clamp_min_nan(s0, scale_floor<DT>()) : s0;
 }
 
 // nvfp_quant.py:85-111.  Block statistic whose |.| maximum over the tensor is the global amax.
@@ -146,13 +151,27 @@ __device__ __forceinline__ void nvfp_block_stat(float mx, float mn, float amax, 
   }
 }
 // s32 = g / (448 * 6) stays fp32 (0-dim / 0-dim); the fp8 block scale is rounded in DT
-template <int DT>
+template <int DT, bool CLAMP = true>
 __device__ __forceinline__ float nvfp_scale(float v, float g_amax, const Fmt& f) {
   const Fmt f8 = make_fmt(LCB_E_FP8_E4M3);
   float s32 = __fdiv_rn(g_amax, __fmul_rn(f8.max_norm, f.max_norm));
   float m = R<DT>(__fdiv_rn(v, __fmul_rn(s32, f.max_norm)));
   float s8 = elem_core<DT>(m, f8);
-  return clamp_min_nan(R<DT>(__fmul_rn(s8, s32)), scale_floor<DT>());
+  const float s0 = R<DT>(__fmul_rn(s8, s32));
+  return CLAMP ? clamp_min_nan(s0, scale_floor<DT>()) : s0;
+}
+
+// parameters before the final clamp (candidates of the mse clip search); NVFP: symmetric only, nv_gamax = the
+// (shrunken) whole-tensor amax
+template <int DT>
+__device__ __forceinline__ void find_params_unclamped(const QCfg& c, float mx, float mn, float amax, float nv_gamax,
+                                                      float& s, float& z) {
+  switch (c.qtype) {
+    case LCB_Q_INT: int_params<DT, DT, false>(mx, mn, amax, c.zero_point, c.f, s, z); break;
+    case LCB_Q_FP: fp_params<DT, DT, false>(mx, mn, amax, c.zero_point, c.f, s, z); break;
+    case LCB_Q_MX: mx_params<DT, false>(mx, mn, amax, c, s, z); break;
+    default: s = nvfp_scale<DT, false>(amax, nv_gamax, c.f); z = 0.0f; break;
+  }
 }
 
 template <int DT, int PDT>

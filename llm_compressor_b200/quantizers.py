@@ -187,8 +187,8 @@ class BaseQuantizer(nn.Module):  # ref: quantizers/base.py:8
         self.group_size = group_size
         self.axes = axes
 
-    def _cfg(self):
-        return _lib.make_cfg(self._QTYPE, self.format.value, self.zero_point, self.scale_ebits)
+    def _cfg(self, mse=False):
+        return _lib.make_cfg(self._QTYPE, self.format.value, self.zero_point, self.scale_ebits, mse=mse)
 
     def _resolve_group(self, x):
         """group_size -1 / -2 become concrete on first use, like the reference (int_quant.py:82-85)."""
@@ -199,16 +199,15 @@ class BaseQuantizer(nn.Module):  # ref: quantizers/base.py:8
         if isinstance(self.group_size, (list, tuple)):
             raise NotImplementedError("2-D block quantisation is commented out in the reference (utils.py:86-91)")
 
-    def _no_mse(self):
-        if self.mse:
-            raise NotImplementedError(
-                "mse clip search (ref: int_quant.py:115-162) is a NEXT row (SURVEY 8f-2) and not built yet")
+    def _mse(self):
+        """mse clip search (ref: int_quant.py:115-162): INT / FP / MX / symmetric NVFP along the last axis; the
+        kernel refuses the rest (LCB_ERR_UNSUPPORTED)."""
+        return bool(self.mse)
 
     def find_params(self, x, already_reshaped=False):
-        self._no_mse()
         if self.group_size != 0 and not already_reshaped:
             self._resolve_group(x)
-        _, s, z, _ = qdq_raw(self._cfg(), x, self.axes, self.group_size, True, False, check_nan=self.check_nan,
+        _, s, z, _ = qdq_raw(self._cfg(self._mse()), x, self.axes, self.group_size, True, False, check_nan=self.check_nan,
                              blocked=bool(already_reshaped and self.group_size != 0))
         return s, z
 
@@ -221,8 +220,8 @@ class BaseQuantizer(nn.Module):  # ref: quantizers/base.py:8
             s, z = self._given_params(x, scales, zeros)
             out, _, _, _ = qdq_raw(self._cfg(), x, self.axes, self.group_size, False, True, scales=s, zeros=z)
         else:
-            self._no_mse()
-            out, _, _, _ = qdq_raw(self._cfg(), x, self.axes, self.group_size, True, True, check_nan=self.check_nan)
+            out, _, _, _ = qdq_raw(self._cfg(self._mse()), x, self.axes, self.group_size, True, True,
+                                   check_nan=self.check_nan)
         if self.is_profile:
             self.record_stats(x=x, qdq_x=out)
         return out

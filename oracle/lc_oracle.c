@@ -162,7 +162,7 @@ static stats_t group_stats(const float* x, long n_valid, long n_group) {
 /* dt: dtype of the tensor (first tensor-tensor op); pdt: dtype of the parameter arithmetic.  They
  * differ only for per-tensor quantisation, where max/min are 0-dim tensors and torch's type
  * promotion (0-dim bf16 op 0-dim fp32 buffer -> fp32) keeps scales / zeros in fp32. */
-static void int_params(stats_t st, int zero_point, float qmax, int dt, int pdt, float* s_out, float* z_out) {
+static void int_params(stats_t st, int zero_point, float qmax, int dt, int pdt, float* s_out, float* z_out, int clamp) {
   float s, z;
   if (zero_point) {
     float range = R(f_sub(st.mx, st.mn), dt);
@@ -173,12 +173,12 @@ static void int_params(stats_t st, int zero_point, float qmax, int dt, int pdt, 
     s = R(f_div(st.amax, qmax), pdt);
     z = 0.0f;
   }
-  *s_out = clamp_min(s, scale_floor(pdt));
+  *s_out = clamp ? clamp_min(s, scale_floor(pdt)) : s;
   *z_out = z;
 }
 
 /* fp_quant.py:102-124,176 */
-static void fp_params(stats_t st, int zero_point, float max_norm, int dt, int pdt, float* s_out, float* z_out) {
+static void fp_params(stats_t st, int zero_point, float max_norm, int dt, int pdt, float* s_out, float* z_out, int clamp) {
   float s, z;
   if (zero_point) {
     float range = R(f_sub(st.mx, st.mn), dt);
@@ -188,7 +188,7 @@ static void fp_params(stats_t st, int zero_point, float max_norm, int dt, int pd
     s = R(f_div(st.amax, max_norm), pdt);
     z = 0.0f;
   }
-  *s_out = clamp_min(s, scale_floor(pdt));
+  *s_out = clamp ? clamp_min(s, scale_floor(pdt)) : s;
   *z_out = z;
 }
 
@@ -204,7 +204,7 @@ static float mx_scale(float val, int emax_elem, int scale_ebits, int dt) {
   return R(powf(2.0f, se), dt);
 }
 
-static void mx_params(stats_t st, int zero_point, fmt_t f, int scale_ebits, int dt, float* s_out, float* z_out) {
+static void mx_params(stats_t st, int zero_point, fmt_t f, int scale_ebits, int dt, float* s_out, float* z_out, int clamp) {
   float s, z;
   if (zero_point) {
     z = R(f_div(R(f_add(st.mx, st.mn), dt), 2.0f), dt);
@@ -213,7 +213,7 @@ static void mx_params(stats_t st, int zero_point, fmt_t f, int scale_ebits, int 
     z = 0.0f;
     s = mx_scale(st.amax, f.emax, scale_ebits, dt);
   }
-  *s_out = clamp_min(s, scale_floor(dt));
+  *s_out = clamp ? clamp_min(s, scale_floor(dt)) : s;
   *z_out = z;
 }
 
@@ -244,14 +244,15 @@ static float fp_fq(float x, float s, float z, fmt_t f, int dt, float* code) {
  */
 int orc_qdq_rows(const float* x, float* out, float* scales, float* zeros, float* codes,
                  long rows, long cols, long group, int qtype, int elem, int zero_point,
-                 int scale_ebits, int dt, int pdt, int params_given, float nv_global) {
+                 int scale_ebits, int dt, int pdt, int params_given, float nv_global, int mse) {
   if (group <= 0) return -1;
+  if (mse && ((qtype == Q_NVFP && zero_point) || cols % group != 0)) return -2;
   fmt_t f = get_fmt(elem);
   long G = (cols + group - 1) / group;
   float qmax = f.max_norm * ldexpf(1.0f, f.mbits - 2); /* int_quant.py:55-57 */
   float* blockmax = NULL;
   float* zbuf = NULL;
-  float s32 = 0.0f;
+  float s32 = 0.0f, gmax_saved = 0.0f;
   fmt_t f8 = get_fmt(F_FP8_E4M3);
 
   if (!params_given && qtype == Q_NVFP) {
@@ -272,6 +273,7 @@ int orc_qdq_rows(const float* x, float* out, float* scales, float* zeros, float*
         g = nmax(g, fabsf(v));
       }
     if (nv_global == nv_global) g = nv_global;
+    gmax_saved = g;
     s32 = f_div(g, f_mul(f8.max_norm, f.max_norm)); /* fp32 even for bf16 tensors (0-dim / 0-dim) */
   }
 
@@ -283,16 +285,74 @@ int orc_qdq_rows(const float* x, float* out, float* scales, float* zeros, float*
       if (params_given) {
         s = scales[r * G + b]; z = zeros[r * G + b];
       } else {
-        if (qtype == Q_NVFP) {
+        if (qtype == Q_NVFP && mse) {
+          /* nvfp_quant.py:113-148 (symmetric): candidate i shrinks every block maximum by p, so the tensor-wide
+           * amax inside _get_scales shrinks to R(p * g) too (rounding is monotone) */
+          float g = gmax_saved;
+          float best = INFINITY;
+          float v = blockmax[r * G + b];
+          z = 0.0f;
+          {
+            float m = R(f_div(v, f_mul(s32, f.max_norm)), dt);
+            s = R(f_mul(elem_core(m, f8, dt), s32), dt);
+          }
+          for (int it = 0; it < 80; ++it) {
+            float p = (float)(1.0 - (double)it / 100.0);
+            float v1 = R(f_mul(v, p), dt), g1 = R(f_mul(g, p), dt);
+            float s32_1 = f_div(g1, f_mul(f8.max_norm, f.max_norm));
+            float m1 = R(f_div(v1, f_mul(s32_1, f.max_norm)), dt);
+            float sc1 = R(f_mul(elem_core(m1, f8, dt), s32_1), dt);
+            float acc = 0.0f;
+            for (long i = 0; i < nv; ++i) {
+              float dq = fp_fq(xg[i], sc1, 0.0f, f, dt, NULL);
+              float d = fabsf(R(f_sub(dq, xg[i]), dt));
+              acc = f_add(acc, R(powf(d, R(2.4f, dt)), dt));
+            }
+            float err = R(acc, dt);
+            if (err < best) { best = err; s = sc1; }
+          }
+          s = clamp_min(s, scale_floor(dt));
+        } else if (qtype == Q_NVFP) {
           float m = R(f_div(blockmax[r * G + b], f_mul(s32, f.max_norm)), dt);
           float s8 = elem_core(m, f8, dt);
           s = clamp_min(R(f_mul(s8, s32), dt), scale_floor(dt));
           z = zbuf[r * G + b];
         } else {
           stats_t st = group_stats(xg, nv, group);
-          if (qtype == Q_INT) int_params(st, zero_point, qmax, dt, pdt, &s, &z);
-          else if (qtype == Q_FP) fp_params(st, zero_point, f.max_norm, dt, pdt, &s, &z);
-          else mx_params(st, zero_point, f, scale_ebits, dt, &s, &z);
+          if (!mse) {
+            if (qtype == Q_INT) int_params(st, zero_point, qmax, dt, pdt, &s, &z, 1);
+            else if (qtype == Q_FP) fp_params(st, zero_point, f.max_norm, dt, pdt, &s, &z, 1);
+            else mx_params(st, zero_point, f, scale_ebits, dt, &s, &z, 1);
+          } else {
+            /* _clip_range (int_quant.py:115-162, fp_quant.py:127-174, mx_quant.py:114-149): 80 shrink steps,
+             * candidate parameters NOT clamped, error |dq - x|^2.4 op by op in the tensor dtype, summed in
+             * fp32 and rounded once; strict < keeps the first minimum; clamp(min=1e-5) at the very end. */
+            if (!zero_point) { st.mx = st.amax; st.mn = -st.amax; }
+            float best = INFINITY;
+            if (qtype == Q_INT) int_params(st, zero_point, qmax, dt, pdt, &s, &z, 0);
+            else if (qtype == Q_FP) fp_params(st, zero_point, f.max_norm, dt, pdt, &s, &z, 0);
+            else mx_params(st, zero_point, f, scale_ebits, dt, &s, &z, 0);
+            for (int it = 0; it < 80; ++it) {
+              float p = (float)(1.0 - (double)it / 100.0);
+              stats_t s1;
+              s1.mx = R(f_mul(st.mx, p), dt); s1.mn = R(f_mul(st.mn, p), dt); s1.amax = s1.mx;
+              float sc1, z1;
+              if (qtype == Q_INT) int_params(s1, zero_point, qmax, dt, pdt, &sc1, &z1, 0);
+              else if (qtype == Q_FP) fp_params(s1, zero_point, f.max_norm, dt, pdt, &sc1, &z1, 0);
+              else mx_params(s1, zero_point, f, scale_ebits, dt, &sc1, &z1, 0);
+              float acc = 0.0f;
+              for (long i = 0; i < nv; ++i) {
+                float dq = (qtype == Q_INT) ? int_fq(xg[i], sc1, z1, qmax, dt, NULL) : fp_fq(xg[i], sc1, z1, f, dt, NULL);
+                float d = fabsf(R(f_sub(dq, xg[i]), dt));
+                /* pow_(2.4) on a bf16 tensor: torch casts the python exponent to the tensor dtype first
+                 * (bf16(2.4) = 2.40625) [measured against the reference on CPU: 8.0e-7 vs 8.3e-7 at 2.93e-3] */
+                acc = f_add(acc, R(powf(d, R(2.4f, dt)), dt));
+              }
+              float err = R(acc, dt);
+              if (err < best) { best = err; s = sc1; z = z1; }
+            }
+            s = clamp_min(s, scale_floor(pdt));
+          }
         }
         if (scales) scales[r * G + b] = s;
         if (zeros) zeros[r * G + b] = z;

@@ -50,7 +50,7 @@ def lib():
         L.orc_qdq_rows.restype = ctypes.c_int
         L.orc_qdq_rows.argtypes = [fp, fp, fp, fp, fp, ctypes.c_long, ctypes.c_long, ctypes.c_long,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                   ctypes.c_int, ctypes.c_int, ctypes.c_float]
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]
         L.orc_elem_core.restype = None
         L.orc_elem_core.argtypes = [fp, fp, ctypes.c_long, ctypes.c_int, ctypes.c_int]
         L.orc_mask_wanda.restype = None
@@ -92,13 +92,14 @@ def elem_core(a, elem, dt):
     return out
 
 
-def qdq(x, cfg, dt, scales=None, zeros=None, want_codes=False, only_params=False):
+def qdq(x, cfg, dt, scales=None, zeros=None, want_codes=False, only_params=False, mse=False):
     """Fake-quantize like `quantizer(x)` / `quantizer.find_params(x)` of the reference.
 
     x: float32 ndarray (bf16-representable when dt == BF16) of rank >= 2 (rank >= 1 per-tensor).
     cfg: reference config dict (type, format, group_size, axes, zero_point[, scale_ebits]).
     Returns (out, scales, zeros, codes); scales/zeros are block-shaped like the reference's
     ([..., G, 1] for axes=-1, [..., G, 1, C] for axes=-2, 0-dim for per-tensor).
+    mse=True: find_params with the clip search (quantizer.mse = True; INT / FP / MX, axes=-1).
     """
     x = np.ascontiguousarray(x, dtype=np.float32)
     qt, el = QTYPES[cfg["type"]], ELEMS[cfg["format"]]
@@ -153,8 +154,8 @@ def qdq(x, cfg, dt, scales=None, zeros=None, want_codes=False, only_params=False
     out = None if only_params else np.empty_like(view)
     codes = np.empty_like(view) if (want_codes and not only_params) else None
     rc = lib().orc_qdq_rows(_fp(view), _fp(out), _fp(s), _fp(z), _fp(codes), rows, cols, group, qt, el, zp,
-                            sebits, dt, F32 if gs == 0 else dt, 1 if given else 0, float("nan"))
-    assert rc == 0
+                            sebits, dt, F32 if gs == 0 else dt, 1 if given else 0, float("nan"), 1 if mse else 0)
+    assert rc == 0, rc
     if gs == 0:
         s_out, z_out = s.reshape(()), z.reshape(())
     elif axes == -1:
