@@ -166,6 +166,15 @@ size_t lcb_gptq_ws_bytes(int64_t n, int64_t k, int block);
 int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, const float* U, const float* P, const float* scales,
                     const float* zeros, const uint8_t* keep, int64_t n, int64_t k, int64_t group, int block,
                     void* ws, size_t ws_bytes, void* stream);
+/* Entry / exit of update_weight around the block loop, one pass over the weight each:
+ * lcb_gptq_gather  (ref: gptq/core.py:164-201): Wp[:, j] = float(W[:, col_perm[j]]), keep = (that != 0), then the
+ *   dead columns (dead[col] != 0, from lcb_hessian_dead_fix) are zeroed in Wp.  W: [n, k] `dtype`; col_perm [k]
+ *   int64 or NULL (identity: no act-order); dead [k] uint8 or NULL.
+ * lcb_gptq_scatter (ref: gptq/core.py:267-278): out[:, col_perm[j]] = cast(Q[:, j]) -- inverse permutation and the
+ *   cast back to the weight dtype. */
+int lcb_gptq_gather(const void* W, int dtype, const int64_t* col_perm, const uint8_t* dead, float* Wp, uint8_t* keep,
+                    int64_t n, int64_t k, void* stream);
+int lcb_gptq_scatter(const float* Q, const int64_t* col_perm, void* out, int dtype, int64_t n, int64_t k, void* stream);
 /* P = alpha * triu(dXXT @ U^T, 1) @ U   (ref: gptaq/core.py:272); dXXT is left untouched */
 size_t lcb_gptaq_p_ws_bytes(int64_t k);
 int lcb_gptaq_p(float* P, float* dxxt, const float* U, int64_t k, float alpha, void* ws, size_t ws_bytes, void* stream);

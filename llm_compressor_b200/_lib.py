@@ -128,6 +128,8 @@ _OPTIONAL = [
     ("lcb_chol_inv_upper", [_vp, _vp, _i64, _vp, _f32, _vp, _sz, _vp, _vp], _i32),
     ("lcb_gptq_ws_bytes", [_i64, _i64, _i32], _sz),
     ("lcb_gptq_update", [_cfgp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, _vp], _i32),
+    ("lcb_gptq_gather", [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _vp], _i32),
+    ("lcb_gptq_scatter", [_vp, _vp, _vp, _i32, _i64, _i64, _vp], _i32),
     ("lcb_gptaq_p_ws_bytes", [_i64], _sz),
     ("lcb_gptaq_p", [_vp, _vp, _vp, _i64, _f32, _vp, _sz, _vp], _i32),
     ("lcb_sparsegpt_ws_bytes", [_i64, _i64, _i32], _sz),

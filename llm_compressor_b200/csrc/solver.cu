@@ -397,6 +397,68 @@ extern "C" int lcb_gptq_update(const lcb_quant_cfg* cfg, float* W, float* Q, con
   return run_block_loop(a, MODE_QUANT, W, U, P, n, k, static_cast<float*>(ws), st, [](int64_t, int) { return LCB_OK; });
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Entry / exit of update_weight around the block loop, each one pass over the weight:
+//   gather : W = weight.float(); MASK = W != 0; W[:, dead] = 0; act-order column permutation
+//            (ref: gptq/core.py:164-201) -> permuted fp32 work matrix + keep mask
+//   scatter: inverse permutation + cast back to the weight dtype (ref: gptq/core.py:267-278)
+namespace lcb {
+template <typename T>
+__global__ void __launch_bounds__(256) gptq_gather_kernel(const T* __restrict__ W, const int64_t* __restrict__ col_perm,
+                                                          const uint8_t* __restrict__ dead, float* __restrict__ Wp,
+                                                          uint8_t* __restrict__ keep, int64_t n, int64_t k) {
+  const int64_t total = n * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k, j = i - r * k;
+    const int64_t src = col_perm ? col_perm[j] : j;
+    const float v = to_f<T>(W[r * k + src]);
+    keep[i] = v != 0.0f;  // MASK is taken before the dead columns are zeroed (ref :166-177)
+    Wp[i] = (dead && dead[src]) ? 0.0f : v;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gptq_scatter_kernel(const float* __restrict__ Q, const int64_t* __restrict__ col_perm,
+                                                           T* __restrict__ out, int64_t n, int64_t k) {
+  const int64_t total = n * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k, j = i - r * k;
+    const int64_t dst = col_perm ? col_perm[j] : j;
+    out[r * k + dst] = from_f<T>(Q[i]);
+  }
+}
+}  // namespace lcb
+
+extern "C" int lcb_gptq_gather(const void* W, int dtype, const int64_t* col_perm, const uint8_t* dead, float* Wp,
+                               uint8_t* keep, int64_t n, int64_t k, void* stream) {
+  LCB_REQUIRE(W && Wp && keep && n > 0 && k > 0, "lcb_gptq_gather: bad arguments");
+  LCB_REQUIRE(dtype == LCB_F32 || dtype == LCB_BF16, "lcb_gptq_gather: dtype must be LCB_F32 or LCB_BF16");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t g = ceil_div(n * k, 256 * 8);
+  if (g > (int64_t)sm_count() * 16) g = (int64_t)sm_count() * 16;
+  if (dtype == LCB_BF16)
+    gptq_gather_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(W), col_perm, dead, Wp,
+                                                                     keep, n, k);
+  else
+    gptq_gather_kernel<float><<<(unsigned)g, 256, 0, st>>>(static_cast<const float*>(W), col_perm, dead, Wp, keep, n, k);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_gptq_scatter(const float* Q, const int64_t* col_perm, void* out, int dtype, int64_t n, int64_t k,
+                                void* stream) {
+  LCB_REQUIRE(Q && out && n > 0 && k > 0, "lcb_gptq_scatter: bad arguments");
+  LCB_REQUIRE(dtype == LCB_F32 || dtype == LCB_BF16, "lcb_gptq_scatter: dtype must be LCB_F32 or LCB_BF16");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t g = ceil_div(n * k, 256 * 8);
+  if (g > (int64_t)sm_count() * 16) g = (int64_t)sm_count() * 16;
+  if (dtype == LCB_BF16)
+    gptq_scatter_kernel<__nv_bfloat16><<<(unsigned)g, 256, 0, st>>>(Q, col_perm, static_cast<__nv_bfloat16*>(out), n, k);
+  else
+    gptq_scatter_kernel<float><<<(unsigned)g, 256, 0, st>>>(Q, col_perm, static_cast<float*>(out), n, k);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
 // P = alpha * triu(dXXT @ U^T, 1) @ U   (ref: gptaq/core.py:272)
 namespace lcb {
 __global__ void triu1_scale_kernel(float* A, int64_t k, float alpha) {

@@ -151,6 +151,39 @@ def gptq_block_update(cfg, W, U, scales, zeros, keep, group, P=None, block=128):
     return Q
 
 
+def gptq_gather(W, col_perm=None, dead=None):
+    """W [n, k] (bf16 / fp32 weight) -> (Wp fp32 [n, k] with columns permuted and dead columns zeroed, keep uint8):
+    `W.float()`, `MASK = W != 0`, `W[:, dead] = 0` and the act-order gather of gptq/core.py:164-201 in one pass."""
+    _need_cuda(W, col_perm, dead)
+    assert W.dim() == 2 and W.is_contiguous()
+    n, k = W.shape
+    Wp = torch.empty((n, k), dtype=torch.float32, device=W.device)
+    keep = torch.empty((n, k), dtype=torch.uint8, device=W.device)
+    if col_perm is not None:
+        col_perm = col_perm.to(torch.int64).contiguous()
+    if dead is not None:
+        dead = dead.to(torch.uint8).contiguous() if dead.dtype != torch.bool else dead.contiguous().view(torch.uint8)
+    with torch.cuda.device(W.device):
+        rc = _lib.lib().lcb_gptq_gather(_ptr(W), _wdt(W), _ptr(col_perm), _ptr(dead), _ptr(Wp), _ptr(keep), n, k,
+                                         _stream(W.device))
+    _lib.check(rc, "lcb_gptq_gather")
+    return Wp, keep
+
+
+def gptq_scatter(Q, col_perm, dtype):
+    """out[:, col_perm[j]] = Q[:, j] cast to `dtype` (inverse act-order permutation + cast, gptq/core.py:267-278)."""
+    _need_cuda(Q, col_perm)
+    assert Q.dtype == torch.float32 and Q.is_contiguous()
+    n, k = Q.shape
+    out = torch.empty((n, k), dtype=dtype, device=Q.device)
+    if col_perm is not None:
+        col_perm = col_perm.to(torch.int64).contiguous()
+    with torch.cuda.device(Q.device):
+        rc = _lib.lib().lcb_gptq_scatter(_ptr(Q), _ptr(col_perm), _ptr(out), _wdt(out), n, k, _stream(Q.device))
+    _lib.check(rc, "lcb_gptq_scatter")
+    return out
+
+
 def gptaq_p(dxxt, U, alpha):
     """P = alpha * triu(dXXT @ U^T, 1) @ U (ref: gptaq/core.py:272); dxxt is left untouched."""
     _need_cuda(dxxt, U)

@@ -105,26 +105,17 @@ def factorize(H, group_size, actorder=True, percdamp=0.01, dXXT=None, alpha=0.25
 
 
 def _solve(q, W, factor, block_size):
-    """GPTQ / GPTAQ solve of one fp32 weight matrix W [N, K] (rows = outputs) with quantizer q and a
-    ready Factor; returns the dequantised result [N, K] fp32 in the original column order."""
-    keep = (W != 0).to(torch.uint8)
+    """GPTQ / GPTAQ solve of one weight matrix W [N, K] (rows = outputs; bf16 or fp32, not modified) with quantizer
+    q and a ready Factor; returns the dequantised result [N, K] in W's dtype and the original column order."""
     N, K = W.shape
     group_size = factor.group_size
-    W.masked_fill_(factor.dead.unsqueeze(0), 0)
-
     per_col = group_size in (0, -1)
-    if factor.perm is None or per_col:
-        scales, zeros = q.find_params(W)  # per-column: NOT recomputed after the permutation (ref :179-185)
-    if factor.perm is not None:
-        if per_col:
-            W = W[:, factor.perm].contiguous()
-            keep = keep[:, factor.perm].contiguous()
-        else:
-            ng = K // group_size
-            W = W.reshape(N, ng, group_size)[:, factor.perm, :].reshape(N, K).contiguous()
-            keep = keep.reshape(N, ng, group_size)[:, factor.perm, :].reshape(N, K).contiguous()
-            scales, zeros = q.find_params(W)  # static groups of the re-ordered W (ref :198)
-
+    # W.float(), MASK = W != 0, W[:, dead] = 0 and the act-order gather in one pass (ref: gptq/core.py:164-201)
+    Wp, keep = ops.gptq_gather(W.contiguous(), factor.col_perm, factor.dead)
+    # per-column branch: the reference takes the per-row parameters before the permutation (ref :179-185); row
+    # max / min do not depend on the column order, so the permuted matrix gives the same values.  Grouped branch:
+    # static groups of the re-ordered W (ref :198).
+    scales, zeros = q.find_params(Wp)
     if per_col:
         s2 = scales.float().reshape(-1, 1).expand(N, 1).contiguous()
         z2 = zeros.float().reshape(-1, 1).expand(N, 1).contiguous()
@@ -133,27 +124,22 @@ def _solve(q, W, factor, block_size):
         s2 = scales.float().reshape(N, K // group_size).contiguous()
         z2 = zeros.float().reshape(N, K // group_size).contiguous()
         grp = group_size
-    Q = ops.gptq_block_update(q._cfg(), W, factor.U, s2, z2, keep, grp, P=factor.P, block=block_size)
-
-    if factor.perm is not None:
-        if per_col:
-            Q = Q[:, factor.invperm]
-        else:
-            Q = Q.reshape(N, K // group_size, group_size)[:, factor.invperm, :].reshape(N, K)
-    return Q
+    Q = ops.gptq_block_update(q._cfg(), Wp, factor.U, s2, z2, keep, grp, P=factor.P, block=block_size)
+    # inverse permutation + cast back to the weight dtype (ref :267-278)
+    return ops.gptq_scatter(Q, factor.col_perm, W.dtype)
 
 
 def _layer_w(layer):
-    W = layer.weight.data.clone()
+    W = layer.weight.data
     if _is_conv1d(layer):
         W = W.t()
-    return W.float().contiguous()
+    return W.contiguous()
 
 
 def _store_w(layer, Q):
     if _is_conv1d(layer):
         Q = Q.t()
-    layer.weight.data = Q.reshape(layer.weight.shape).to(layer.weight.data.dtype)
+    layer.weight.data = Q.reshape(layer.weight.shape).to(layer.weight.data.dtype).contiguous()
 
 
 def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, factor=None):
@@ -185,7 +171,7 @@ def update_weights_shared(layers, device, factor, block_size=128):
             _update_weight(l, device, block_size, 0.01, True, factor=factor)
         return
     sizes = [l.weight.shape[0] for l in layers]
-    W = torch.cat([l.weight.data for l in layers], 0).float().contiguous()
+    W = torch.cat([l.weight.data for l in layers], 0).contiguous()
     for l in layers:
         for attr in ("H", "dXXT"):
             if hasattr(l.weight_quantizer, attr):
