@@ -477,12 +477,7 @@ __global__ void put_diag_blocks_kernel(float* A, int64_t k, const float* dinv_al
 
 }  // namespace
 
-// Two side streams + events per host thread and device for the look-ahead of the tensor-core Cholesky.
-struct SideStreams {
-  cudaStream_t s[2];
-  cudaEvent_t evP, evB[2], evS[2];
-};
-static SideStreams* side_streams() {
+SideStreams* side_streams() {
   static thread_local SideStreams cache[16];
   static thread_local bool ready[16] = {false};
   int dev = 0;

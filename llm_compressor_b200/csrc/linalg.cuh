@@ -62,4 +62,13 @@ inline bool tg_ok(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_
 // solver GEMM precision: 0 = exact fp32 FFMA (sgemm), 1 = 3xTF32 on tcgen05 (default)
 int gemm_mode();
 
+// Two library-owned side streams + events per host thread and device: look-ahead of the latency-bound chains
+// (Cholesky panels, GPTQ block steps) -- the update the next step needs stays on the caller's stream, the rest
+// runs underneath the following steps.  nullptr (and lcb_last_error set) when they cannot be created.
+struct SideStreams {
+  cudaStream_t s[2];
+  cudaEvent_t evP, evB[2], evS[2];
+};
+SideStreams* side_streams();
+
 }  // namespace lcb

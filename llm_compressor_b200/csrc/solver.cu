@@ -271,7 +271,7 @@ static int64_t super_cols(int64_t k) { return std::min<int64_t>(SUPER, ceil_div(
 
 static size_t gptq_ws_floats(int64_t n, int64_t k, int block) {
   const size_t exact = (size_t)(2 * n * block);
-  const size_t tg = (size_t)(4 * n * super_cols(k)) + (size_t)(4 * k * k);
+  const size_t tg = (size_t)(8 * n * super_cols(k)) + (size_t)(4 * k * k);
   return std::max(exact, tg) + 64;
 }
 
@@ -322,49 +322,86 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
     }
     return LCB_OK;
   }
-  // ---- tensor-core path
+  // ---- tensor-core path with look-ahead (same scheme as the Cholesky panels, chol.cu): the block steps are a
+  // latency-bound chain; after each step only the NEXT block's columns are updated on the caller's stream, the
+  // rest of the super-block (and, per super-block, everything beyond the next one) on side streams underneath
+  // the following steps.  All updates are L2 reduce-adds (they commute); events order them against the readers;
+  // the error planes are double-buffered per super-block.
   const int64_t S = super_cols(k);
-  float* ErrH = wsf;
-  float* ErrL = ErrH + n * S;
-  float* W1H = ErrL + n * S;
-  float* W1L = W1H + n * S;
-  float* UTh = W1L + n * S;
+  float* planes = wsf;                       // [parity][ErrH | ErrL | W1H | W1L][n, S]
+  float* UTh = wsf + 8 * n * S;
   float* UTl = UTh + k * k;
   float* PTh = UTl + k * k;
   float* PTl = PTh + k * k;
   if ((rc = split_tf32(U, k, (int)k, (int)k, UTh, UTl, k, /*transpose=*/1, st)) != LCB_OK) return rc;
   if (P && (rc = split_tf32(P, k, (int)k, (int)k, PTh, PTl, k, 1, st)) != LCB_OK) return rc;
-  a.Err = ErrH; a.ErrLo = ErrL; a.ldE = S;
-  a.W1out = P ? W1H : nullptr; a.W1Lo = P ? W1L : nullptr;
-  for (int64_t s0 = 0; s0 < k; s0 += S) {
+  SideStreams* ss = side_streams();
+  if (ss == nullptr) return LCB_ERR_CUDA;
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(ss->s[0]);
+    cudaStreamSynchronize(ss->s[1]);
+    return code;
+  };
+  // C[:, c0 : c0 + ncols] -= Err[:, e0 : e0 + kd] @ U[i1 + .., c0 ..]  (+ W1 @ P) on stream `s`
+  auto update = [&](float* EH, float* EL, float* WH, float* WL, int64_t e0, int64_t urow, int64_t c0, int64_t ncols,
+                    int kd, cudaStream_t s) -> int {
+    int r = tgemm_nt(EH + e0, EL + e0, S, UTh + c0 * k + urow, UTl + c0 * k + urow, k, W + c0, k, (int)n, (int)ncols, kd,
+                     -1.0f, 0, s);
+    if (r != LCB_OK || !P) return r;
+    return tgemm_nt(WH + e0, WL + e0, S, PTh + c0 * k + urow, PTl + c0 * k + urow, k, W + c0, k, (int)n, (int)ncols, kd,
+                    1.0f, 0, s);
+  };
+  bool evB_live[2] = {false, false}, evS_live[2] = {false, false};
+  int64_t q = 0, J = 0;
+  for (int64_t s0 = 0; s0 < k; s0 += S, ++J) {
     const int64_t s1 = std::min<int64_t>(s0 + S, k);
-    for (int64_t i1 = s0; i1 < s1; i1 += BLK) {
+    float* EH = planes + (J & 1) * 4 * n * S;
+    float* EL = EH + n * S;
+    float* WH = EL + n * S;
+    float* WL = WH + n * S;
+    // this super-block's columns were updated by S_A(J-1) (this stream) and S_B(J-2) (side stream 1), which also
+    // read the planes of parity J & 1; the B updates of earlier super-blocks read the other parity
+    if (evS_live[J & 1]) { LCB_CUDA(cudaStreamWaitEvent(st, ss->evS[J & 1], 0)); evS_live[J & 1] = false; }
+    for (int e = 0; e < 2; ++e)
+      if (evB_live[e]) { LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[e], 0)); evB_live[e] = false; }
+    a.Err = EH; a.ErrLo = EL; a.ldE = S;
+    a.W1out = P ? WH : nullptr; a.W1Lo = P ? WL : nullptr;
+    for (int64_t i1 = s0; i1 < s1; i1 += BLK, ++q) {
       const int64_t i2 = std::min<int64_t>(i1 + BLK, k);
       a.i1 = i1; a.count = (int)(i2 - i1); a.eoff = i1 - s0;
-      if ((rc = pre_block(i1, a.count)) != LCB_OK) return rc;
-      if ((rc = step()) != LCB_OK) return rc;
+      // block q's columns: A(q-1) on this stream, B(q-2) on side stream 0
+      if (evB_live[q & 1]) { LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[q & 1], 0)); evB_live[q & 1] = false; }
+      if ((rc = pre_block(i1, a.count)) != LCB_OK) return fail(rc);
+      if ((rc = step()) != LCB_OK) return fail(rc);
       if (i2 < s1) {  // rest of the super-block, Kd = 128 (short last block: its zero padded columns add 0)
         const int kd = (int)std::min<int64_t>(BLK, S - a.eoff);
-        rc = tgemm_nt(ErrH + a.eoff, ErrL + a.eoff, S, UTh + i2 * k + i1, UTl + i2 * k + i1, k, W + i2, k, (int)n,
-                      (int)(s1 - i2), kd, -1.0f, 0, st);
-        if (rc != LCB_OK) return rc;
-        if (P) {
-          rc = tgemm_nt(W1H + a.eoff, W1L + a.eoff, S, PTh + i2 * k + i1, PTl + i2 * k + i1, k, W + i2, k, (int)n,
-                        (int)(s1 - i2), kd, 1.0f, 0, st);
-          if (rc != LCB_OK) return rc;
+        const int64_t nA = std::min<int64_t>(BLK, s1 - i2), nB = s1 - i2 - nA;
+        if (nB > 0) {  // B(q): beyond the next block, side stream 0
+          LCB_CUDA(cudaEventRecord(ss->evP, st));
+          LCB_CUDA(cudaStreamWaitEvent(ss->s[0], ss->evP, 0));
+          if ((rc = update(EH, EL, WH, WL, a.eoff, i1, i2 + nA, nB, kd, ss->s[0])) != LCB_OK) return fail(rc);
+          LCB_CUDA(cudaEventRecord(ss->evB[q & 1], ss->s[0]));
+          evB_live[q & 1] = true;
         }
+        if ((rc = update(EH, EL, WH, WL, a.eoff, i1, i2, nA, kd, st)) != LCB_OK) return fail(rc);  // A(q)
       }
     }
     if (s1 < k) {  // everything beyond the super-block, Kd = S
-      rc = tgemm_nt(ErrH, ErrL, S, UTh + s1 * k + s0, UTl + s1 * k + s0, k, W + s1, k, (int)n, (int)(k - s1),
-                    (int)(s1 - s0), -1.0f, 0, st);
-      if (rc != LCB_OK) return rc;
-      if (P) {
-        rc = tgemm_nt(W1H, W1L, S, PTh + s1 * k + s0, PTl + s1 * k + s0, k, W + s1, k, (int)n, (int)(k - s1),
-                      (int)(s1 - s0), 1.0f, 0, st);
-        if (rc != LCB_OK) return rc;
+      const int kd = (int)(s1 - s0);
+      const int64_t nA = std::min<int64_t>(S, k - s1), nB = k - s1 - nA;
+      if (nB > 0) {  // S_B(J): beyond the next super-block, side stream 1
+        LCB_CUDA(cudaEventRecord(ss->evP, st));
+        LCB_CUDA(cudaStreamWaitEvent(ss->s[1], ss->evP, 0));
+        if ((rc = update(EH, EL, WH, WL, 0, s0, s1 + nA, nB, kd, ss->s[1])) != LCB_OK) return fail(rc);
+        LCB_CUDA(cudaEventRecord(ss->evS[J & 1], ss->s[1]));
+        evS_live[J & 1] = true;
       }
+      if ((rc = update(EH, EL, WH, WL, 0, s0, s1, nA, kd, st)) != LCB_OK) return fail(rc);  // S_A(J)
     }
+  }
+  for (int e = 0; e < 2; ++e) {
+    if (evB_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[e], 0));
+    if (evS_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evS[e], 0));
   }
   return LCB_OK;
 }
