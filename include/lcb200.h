@@ -184,6 +184,17 @@ size_t lcb_sparsegpt_ws_bytes(int64_t n, int64_t k, int block);
 int lcb_sparsegpt_update(float* W, const float* U, double sparsity, int64_t n, int64_t k, int block, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* Row-sharded variant: this rank holds n_local of the n_total output rows; the per-block threshold
+ * (ref: sparsegpt/core.py:202, the int(numel * sparsity)-th smallest saliency of the [n_total, 128] block) is found
+ * by the same 4-pass radix select, with `reduce(hist, 256, user, stream)` called once per pass to sum the uint32
+ * histograms over the ranks (4 * k/128 calls, each must be ordered on `stream`; e.g. an NCCL all-reduce).  Every rank
+ * then applies the identical threshold to its rows: masks are bit-identical to the unsharded call.
+ * The callback returns 0 on success. */
+typedef int (*lcb_reduce_u32_fn)(void* device_u32, int64_t count, void* user, void* stream);
+int lcb_sparsegpt_update_sharded(float* W, const float* U, double sparsity, int64_t n_local, int64_t n_total, int64_t k,
+                                 int block, void* ws, size_t ws_bytes, lcb_reduce_u32_fn reduce, void* reduce_user,
+                                 void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense contractions of the solvers (lazy-batch update ref: gptq/core.py:265, gptaq/core.py:272,319,
  * sparsegpt/core.py:218; Cholesky trailing updates behind ref: gptq/core.py:213-224).
@@ -218,6 +229,27 @@ int lcb_mask_magnitude(const void* W, int dtype, uint8_t* mask, int64_t n, int64
                        size_t ws_bytes, void* stream);
 int lcb_mask_ria(const void* W, int dtype, const float* scaler_row, uint8_t* mask, int64_t n, int64_t k, double ratio,
                  float alpha, void* ws, size_t ws_bytes, void* stream);
+/* Phase API behind lcb_mask_magnitude / lcb_mask_ria for row-sharded weights.  Exact global k-th
+ * smallest of scores spread over ranks, MSB-first radix select, 4 passes:
+ *     lcb_select_init(state, kth_global)
+ *     for pass in 0..3:  lcb_select_hist(local scores, n_local, state, pass)
+ *                        all-reduce(SUM) of the 256 uint32 counters at byte offset LCB_SELECT_HIST_OFFSET of state
+ *                        lcb_select_scan(state, pass, thresh)         -- same result on every rank
+ *     lcb_mask_le(local scores, thresh, mask)                         -- mask = score <= thresh (ref: `<=`)
+ * state: lcb_select_state_bytes() bytes of device memory.
+ * RIA (ref: ria/core.py:118-126): lcb_ria_sums gives the UNROUNDED fp32 column sums of |W| over the local rows
+ * (all-reduce(SUM) them) and the local row sums rounded to W's dtype; lcb_ria_metric rounds the total column sums to
+ * W's dtype and builds the fp32 scores. */
+#define LCB_SELECT_HIST_OFFSET 16
+size_t lcb_select_state_bytes(void);
+int lcb_select_init(void* state, int64_t kth, void* stream);
+int lcb_select_hist(const float* vals, int64_t n, void* state, int pass, void* stream);
+int lcb_select_scan(void* state, int pass, float* thresh, void* stream);
+int lcb_metric_magnitude(const void* W, int dtype, float* metric, int64_t numel, void* stream);
+int lcb_ria_sums(const void* W, int dtype, float* colsum_partial, float* rowsum, int64_t n, int64_t k, void* stream);
+int lcb_ria_metric(const void* W, int dtype, const float* colsum, const float* rowsum, const float* scaler_row,
+                   float* metric, int64_t n, int64_t k, float alpha, void* stream);
+int lcb_mask_le(const float* metric, const float* thresh, uint8_t* mask, int64_t numel, void* stream);
 /* W[mask] = 0 in place */
 int lcb_apply_mask(void* W, int dtype, const uint8_t* mask, int64_t numel, void* stream);
 

@@ -117,6 +117,7 @@ def lib():
 
 _vp, _i64, _i32, _sz, _f32, _f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_double
 _cfgp = ctypes.POINTER(QuantCfg)
+REDUCE_U32_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p)  # lcb_reduce_u32_fn
 _OPTIONAL = [
     ("lcb_launch_count", [], ctypes.c_uint64),
     ("lcb_hessian_ws_bytes", [_i64, _i64], _sz),
@@ -139,6 +140,15 @@ _OPTIONAL = [
     ("lcb_mask_magnitude", [_vp, _i32, _vp, _i64, _i64, _f64, _vp, _sz, _vp], _i32),
     ("lcb_mask_ria", [_vp, _i32, _vp, _vp, _i64, _i64, _f64, _f32, _vp, _sz, _vp], _i32),
     ("lcb_apply_mask", [_vp, _i32, _vp, _i64, _vp], _i32),
+    ("lcb_sparsegpt_update_sharded", [_vp, _vp, _f64, _i64, _i64, _i64, _i32, _vp, _sz, _vp, _vp, _vp], _i32),
+    ("lcb_select_state_bytes", [], _sz),
+    ("lcb_select_init", [_vp, _i64, _vp], _i32),
+    ("lcb_select_hist", [_vp, _i64, _vp, _i32, _vp], _i32),
+    ("lcb_select_scan", [_vp, _i32, _vp, _vp], _i32),
+    ("lcb_metric_magnitude", [_vp, _i32, _vp, _i64, _vp], _i32),
+    ("lcb_ria_sums", [_vp, _i32, _vp, _vp, _i64, _i64, _vp], _i32),
+    ("lcb_ria_metric", [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp], _i32),
+    ("lcb_mask_le", [_vp, _vp, _vp, _i64, _vp], _i32),
     ("lcb_set_gemm_mode", [_i32], _i32),
     ("lcb_tgemm_ws_bytes", [_i64, _i64, _i64], _sz),
     ("lcb_tgemm_nt", [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp, _sz, _vp], _i32),

@@ -5,6 +5,8 @@
 //      pruning/sparsegpt/core.py:201-203 (k-th value of a [N,128] block, <=).
 // Selection is an MSB-first radix select on order-preserving uint32 keys: exact k-th order
 // statistic in 4 passes of 8 bits; NaN keys sort last like torch.sort.
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace lcb {
@@ -17,6 +19,8 @@ struct SelState {
   unsigned long long krem;
   uint32_t hist[256];
 };
+
+static_assert(offsetof(SelState, hist) == LCB_SELECT_HIST_OFFSET, "lcb200.h documents the histogram offset");
 
 __global__ void sel_init_kernel(SelState* s, unsigned long long kth) {
   if (threadIdx.x == 0) { s->prefix = 0; s->krem = kth; }
@@ -71,7 +75,7 @@ __global__ void le_mask_kernel(const float* __restrict__ m, const float* thresh,
 // ---- RIA statistics: column / row sums of |W| accumulated in fp32, rounded once to W's dtype
 template <typename T>
 __global__ void __launch_bounds__(256) abs_colsum_kernel(const T* __restrict__ w, float* __restrict__ cs, int64_t n,
-                                                         int64_t k) {
+                                                         int64_t k, bool round_out) {
   constexpr int DT = DtOf<T>::value;
   __shared__ float red[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(256) abs_colsum_kernel(const T* __restrict__ w
   __syncthreads();
   if (ty == 0 && c < k) {
     for (int i = 1; i < 8; ++i) s += red[i][tx];
-    cs[c] = R<DT>(s);
+    cs[c] = round_out ? R<DT>(s) : s;  // row-sharded callers all-reduce the fp32 partial sums first
   }
 }
 template <typename T>
@@ -108,7 +112,7 @@ __global__ void ria_metric_kernel(const T* __restrict__ w, const float* __restri
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * k; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / k, c = i - r * k;
     const float a = fabsf(to_f<T>(w[i]));
-    const float t0 = R<DT>(__fdiv_rn(a, cs[c]));
+    const float t0 = R<DT>(__fdiv_rn(a, R<DT>(cs[c])));  // R is idempotent on an already rounded sum
     const float t1 = R<DT>(__fdiv_rn(a, rs[r]));
     const float base = R<DT>(__fadd_rn(t0, t1));
     const float sq = __fsqrt_rn(srow[c]);
@@ -216,7 +220,8 @@ int grid1d(int64_t n) {
 
 size_t select_ws_bytes() { return sizeof(SelState) + 64; }
 
-int select_kth_f32(const float* vals, int64_t n, int64_t kth, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+int select_kth_f32(const float* vals, int64_t n, int64_t kth, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                   lcb_reduce_u32_fn reduce, void* reduce_user) {
   if (ws == nullptr || ws_bytes < select_ws_bytes()) {
     set_error("select_kth_f32: workspace too small");
     return LCB_ERR_WORKSPACE;
@@ -227,6 +232,12 @@ int select_kth_f32(const float* vals, int64_t n, int64_t kth, float* out, void* 
   for (int pass = 0; pass < 4; ++pass) {
     sel_hist_kernel<<<grid1d(n), 256, 0, st>>>(vals, n, s, pass);
     LCB_LAUNCH_CHECK();
+    if (reduce != nullptr) {  // row-sharded scores: sum the histograms over the ranks (enqueued on `st` by the caller)
+      if (reduce(s->hist, 256, reduce_user, st) != 0) {
+        set_error("select_kth_f32: the reduce callback failed");
+        return LCB_ERR_CUDA;
+      }
+    }
     sel_scan_kernel<<<1, 32, 0, st>>>(s, pass, out);
     LCB_LAUNCH_CHECK();
   }
@@ -270,7 +281,7 @@ static int threshold_mask(float* metric, int64_t numel, double ratio, uint8_t* m
                           cudaStream_t st) {
   int64_t kth = (int64_t)((double)numel * ratio);  // int(W.numel() * sparsity_ratio)
   if (kth >= numel) kth = numel - 1;
-  int rc = select_kth_f32(metric, numel, kth, thresh, sel_ws, select_ws_bytes(), st);
+  int rc = select_kth_f32(metric, numel, kth, thresh, sel_ws, select_ws_bytes(), st, nullptr, nullptr);
   if (rc != LCB_OK) return rc;
   le_mask_kernel<<<grid1d(numel), 256, 0, st>>>(metric, thresh, mask, numel);
   LCB_LAUNCH_CHECK();
@@ -297,7 +308,7 @@ extern "C" int lcb_mask_magnitude(const void* W, int dtype, uint8_t* mask, int64
 template <typename T>
 static int ria_typed(const T* W, const float* srow, float* metric, float* cs, float* rs, int64_t n, int64_t k,
                      float alpha, cudaStream_t st) {
-  abs_colsum_kernel<T><<<(unsigned)ceil_div(k, 32), 256, 0, st>>>(W, cs, n, k);
+  abs_colsum_kernel<T><<<(unsigned)ceil_div(k, 32), 256, 0, st>>>(W, cs, n, k, true);
   LCB_LAUNCH_CHECK();
   abs_rowsum_kernel<T><<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(W, rs, n, k);
   LCB_LAUNCH_CHECK();
@@ -324,6 +335,81 @@ extern "C" int lcb_mask_ria(const void* W, int dtype, const float* scaler_row, u
                : ria_typed(static_cast<const float*>(W), scaler_row, metric, cs, rs, n, k, alpha, st);
   if (rc != LCB_OK) return rc;
   return threshold_mask(metric, n * k, ratio, mask, thresh, sel_ws, st);
+}
+
+// ---- phase API for row-sharded global thresholds: the caller all-reduces hist[256] between
+// lcb_select_hist and lcb_select_scan, and the fp32 column sums between lcb_ria_sums and lcb_ria_metric.
+extern "C" size_t lcb_select_state_bytes(void) { return sizeof(SelState); }
+
+extern "C" int lcb_select_init(void* state, int64_t kth, void* stream) {
+  LCB_REQUIRE(state != nullptr && kth >= 0, "lcb_select_init: bad arguments");
+  sel_init_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<SelState*>(state), (unsigned long long)kth);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_select_hist(const float* vals, int64_t n, void* state, int pass, void* stream) {
+  LCB_REQUIRE(state != nullptr && n >= 0 && pass >= 0 && pass < 4 && (vals != nullptr || n == 0), "lcb_select_hist: bad arguments");
+  if (n == 0) return LCB_OK;  // an empty shard contributes nothing
+  sel_hist_kernel<<<grid1d(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(vals, n, static_cast<SelState*>(state), pass);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_select_scan(void* state, int pass, float* thresh, void* stream) {
+  LCB_REQUIRE(state != nullptr && thresh != nullptr && pass >= 0 && pass < 4, "lcb_select_scan: bad arguments");
+  sel_scan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<SelState*>(state), pass, thresh);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_metric_magnitude(const void* W, int dtype, float* metric, int64_t numel, void* stream) {
+  LCB_REQUIRE(numel >= 0 && (numel == 0 || (W && metric)), "lcb_metric_magnitude: bad arguments");
+  if (numel == 0) return LCB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == LCB_BF16) abs_metric_kernel<<<grid1d(numel), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(W), metric, numel);
+  else abs_metric_kernel<<<grid1d(numel), 256, 0, st>>>(static_cast<const float*>(W), metric, numel);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_ria_sums(const void* W, int dtype, float* colsum_partial, float* rowsum, int64_t n, int64_t k,
+                            void* stream) {
+  LCB_REQUIRE(W && colsum_partial && rowsum && n > 0 && k > 0, "lcb_ria_sums: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == LCB_BF16) {
+    const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(W);
+    abs_colsum_kernel<__nv_bfloat16><<<(unsigned)ceil_div(k, 32), 256, 0, st>>>(w, colsum_partial, n, k, false);
+    abs_rowsum_kernel<__nv_bfloat16><<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(w, rowsum, n, k);
+  } else {
+    const float* w = static_cast<const float*>(W);
+    abs_colsum_kernel<float><<<(unsigned)ceil_div(k, 32), 256, 0, st>>>(w, colsum_partial, n, k, false);
+    abs_rowsum_kernel<float><<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(w, rowsum, n, k);
+  }
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_ria_metric(const void* W, int dtype, const float* colsum, const float* rowsum, const float* scaler_row,
+                              float* metric, int64_t n, int64_t k, float alpha, void* stream) {
+  LCB_REQUIRE(W && colsum && rowsum && scaler_row && metric && n > 0 && k > 0, "lcb_ria_metric: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == LCB_BF16)
+    ria_metric_kernel<__nv_bfloat16><<<grid1d(n * k), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(W), colsum, rowsum,
+                                                                   scaler_row, metric, n, k, alpha);
+  else
+    ria_metric_kernel<float><<<grid1d(n * k), 256, 0, st>>>(static_cast<const float*>(W), colsum, rowsum, scaler_row, metric,
+                                                            n, k, alpha);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_mask_le(const float* metric, const float* thresh, uint8_t* mask, int64_t numel, void* stream) {
+  LCB_REQUIRE(thresh && numel >= 0 && (numel == 0 || (metric && mask)), "lcb_mask_le: bad arguments");
+  if (numel == 0) return LCB_OK;
+  le_mask_kernel<<<grid1d(numel), 256, 0, static_cast<cudaStream_t>(stream)>>>(metric, thresh, mask, numel);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
 }
 
 extern "C" int lcb_apply_mask(void* W, int dtype, const uint8_t* mask, int64_t numel, void* stream) {

@@ -253,7 +253,8 @@ __global__ void sparse_mask_kernel(const float* metric, const float* thresh, uin
 }  // namespace
 
 // exact k-th smallest (0-based index `kth`) of n non-negative-or-any fp32 values (masks.cu)
-int select_kth_f32(const float* vals, int64_t n, int64_t kth, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int select_kth_f32(const float* vals, int64_t n, int64_t kth, float* out, void* ws, size_t ws_bytes, cudaStream_t st,
+                   lcb_reduce_u32_fn reduce, void* reduce_user);
 size_t select_ws_bytes();
 
 }  // namespace lcb
@@ -552,9 +553,9 @@ extern "C" size_t lcb_sparsegpt_ws_bytes(int64_t n, int64_t k, int block) {
   return gptq_ws_floats(n, k, block) * sizeof(float) + sparse_tail_bytes(n);
 }
 
-extern "C" int lcb_sparsegpt_update(float* W, const float* U, double sparsity, int64_t n, int64_t k, int block,
-                                    void* ws, size_t ws_bytes, void* stream) {
-  LCB_REQUIRE(W && U && n > 0 && k > 0, "lcb_sparsegpt_update: bad arguments");
+static int sparsegpt_update_impl(float* W, const float* U, double sparsity, int64_t n, int64_t n_total, int64_t k, int block,
+                                 void* ws, size_t ws_bytes, lcb_reduce_u32_fn reduce, void* reduce_user, void* stream) {
+  LCB_REQUIRE(W && U && n > 0 && k > 0 && n_total >= n, "lcb_sparsegpt_update: bad arguments");
   LCB_REQUIRE(block == BLK, "lcb_sparsegpt_update: block must be 128");
   if (ws == nullptr || ws_bytes < lcb_sparsegpt_ws_bytes(n, k, block) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
     set_error("lcb_sparsegpt_update: 16-byte aligned workspace of %zu bytes needed", lcb_sparsegpt_ws_bytes(n, k, block));
@@ -576,13 +577,26 @@ extern "C" int lcb_sparsegpt_update(float* W, const float* U, double sparsity, i
     const int64_t numel = n * count;
     sparse_metric_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, st>>>(W, U, metric, n, k, i1, count);
     LCB_LAUNCH_CHECK();
-    int64_t kth = (int64_t)((double)numel * sparsity);  // int(tmp.numel() * sparsity_ratio)
-    if (kth >= numel) kth = numel - 1;
-    int rc = select_kth_f32(metric, numel, kth, thresh, sel_ws, select_ws_bytes(), st);
+    const int64_t numel_total = n_total * count;  // the block's rows over all ranks
+    int64_t kth = (int64_t)((double)numel_total * sparsity);  // int(tmp.numel() * sparsity_ratio)
+    if (kth >= numel_total) kth = numel_total - 1;
+    int rc = select_kth_f32(metric, numel, kth, thresh, sel_ws, select_ws_bytes(), st, reduce, reduce_user);
     if (rc != LCB_OK) return rc;
     sparse_mask_kernel<<<(unsigned)ceil_div(numel, 256), 256, 0, st>>>(metric, thresh, prune, n, count);
     LCB_LAUNCH_CHECK();
     return LCB_OK;
   };
   return run_block_loop(a, MODE_SPARSE, W, U, nullptr, n, k, wsf, st, pre);
+}
+
+extern "C" int lcb_sparsegpt_update(float* W, const float* U, double sparsity, int64_t n, int64_t k, int block,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  return sparsegpt_update_impl(W, U, sparsity, n, n, k, block, ws, ws_bytes, nullptr, nullptr, stream);
+}
+
+extern "C" int lcb_sparsegpt_update_sharded(float* W, const float* U, double sparsity, int64_t n_local, int64_t n_total,
+                                            int64_t k, int block, void* ws, size_t ws_bytes, lcb_reduce_u32_fn reduce,
+                                            void* reduce_user, void* stream) {
+  LCB_REQUIRE(reduce != nullptr, "lcb_sparsegpt_update_sharded: a reduce callback is required");
+  return sparsegpt_update_impl(W, U, sparsity, n_local, n_total, k, block, ws, ws_bytes, reduce, reduce_user, stream);
 }

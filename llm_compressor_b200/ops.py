@@ -198,8 +198,11 @@ def gptaq_p(dxxt, U, alpha):
     return P
 
 
-def sparsegpt_update(W, U, sparsity, block=128):
-    """Block loop of prune_weight (ref: sparsegpt/core.py:192-218); W [n,k] fp32 updated in place."""
+def sparsegpt_update(W, U, sparsity, block=128, n_total=None, reduce=None):
+    """Block loop of prune_weight (ref: sparsegpt/core.py:192-218); W [n,k] fp32 updated in place.
+    Row-sharded form: W holds this rank's n of the n_total output rows and `reduce(hist)` sums an
+    int32[256] device tensor over the ranks in place (called 4 times per 128-column block, on the current stream);
+    the per-block threshold is then the exact global one and the masks equal the unsharded call's bit for bit."""
     _need_cuda(W, U)
     L = _lib.lib()
     n, k = W.shape
@@ -207,8 +210,28 @@ def sparsegpt_update(W, U, sparsity, block=128):
     ws_bytes = L.lcb_sparsegpt_ws_bytes(n, k, block)
     ws = _ws(ws_bytes, W.device)
     with torch.cuda.device(W.device):
-        rc = L.lcb_sparsegpt_update(_ptr(W), _ptr(U), float(sparsity), n, k, block, _ptr(ws), ws_bytes,
-                                    _stream(W.device))
+        if reduce is None:
+            assert n_total is None or n_total == n
+            rc = L.lcb_sparsegpt_update(_ptr(W), _ptr(U), float(sparsity), n, k, block, _ptr(ws), ws_bytes,
+                                        _stream(W.device))
+        else:
+            base, failure = ws.data_ptr(), []
+
+            def _cb(ptr, count, _user, _stream_):
+                try:
+                    off = int(ptr) - base
+                    assert 0 <= off and off % 4 == 0 and off + 4 * count <= ws_bytes
+                    reduce(ws[off:off + 4 * count].view(torch.int32))
+                    return 0
+                except BaseException as e:  # never let an exception cross the C frame
+                    failure.append(e)
+                    return 1
+
+            cb = _lib.REDUCE_U32_FN(_cb)
+            rc = L.lcb_sparsegpt_update_sharded(_ptr(W), _ptr(U), float(sparsity), n, int(n_total), k, block, _ptr(ws),
+                                                ws_bytes, cb, None, _stream(W.device))
+            if failure:
+                raise failure[0]
     _lib.check(rc, "lcb_sparsegpt_update")
     return W
 
@@ -255,6 +278,87 @@ def mask_magnitude(W, ratio):
 
 def mask_ria(W, scaler_row, ratio, alpha):
     return _mask_call("lcb_mask_ria", W, scaler_row, ratio, alpha)
+
+
+# ---- phase API for row-sharded global thresholds (parallel.py drives the collectives in between)
+SELECT_HIST_OFFSET = 16  # LCB_SELECT_HIST_OFFSET
+
+
+def select_state(device):
+    """Device state of one distributed radix select: (int32 buffer, view of its 256 histogram counters)."""
+    nbytes = int(_lib.lib().lcb_select_state_bytes())
+    buf = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device)
+    return buf, buf[SELECT_HIST_OFFSET // 4: SELECT_HIST_OFFSET // 4 + 256]
+
+
+def select_init(state, kth):
+    _need_cuda(state)
+    with torch.cuda.device(state.device):
+        _lib.check(_lib.lib().lcb_select_init(_ptr(state), int(kth), _stream(state.device)), "lcb_select_init")
+
+
+def select_hist(state, scores, pass_):
+    _need_cuda(state, scores)
+    assert scores.dtype == torch.float32 and scores.is_contiguous()
+    with torch.cuda.device(state.device):
+        _lib.check(_lib.lib().lcb_select_hist(_ptr(scores) if scores.numel() else None, scores.numel(), _ptr(state),
+                                              int(pass_), _stream(state.device)), "lcb_select_hist")
+
+
+def select_scan(state, pass_, thresh):
+    _need_cuda(state, thresh)
+    with torch.cuda.device(state.device):
+        _lib.check(_lib.lib().lcb_select_scan(_ptr(state), int(pass_), _ptr(thresh), _stream(state.device)),
+                   "lcb_select_scan")
+
+
+def metric_magnitude(W):
+    """|W| as fp32 scores (ref: magnitude/core.py:38-39)."""
+    _need_cuda(W)
+    assert W.is_contiguous()
+    m = torch.empty(W.shape, dtype=torch.float32, device=W.device)
+    with torch.cuda.device(W.device):
+        _lib.check(_lib.lib().lcb_metric_magnitude(_ptr(W) if W.numel() else None, _wdt(W), _ptr(m) if W.numel() else None,
+                                                   W.numel(), _stream(W.device)), "lcb_metric_magnitude")
+    return m
+
+
+def ria_sums(W):
+    """(unrounded fp32 column sums of |W| over these rows, row sums rounded to W's dtype) -- ref: ria/core.py:118-121."""
+    _need_cuda(W)
+    assert W.dim() == 2 and W.is_contiguous()
+    n, k = W.shape
+    cs = torch.zeros(k, dtype=torch.float32, device=W.device)
+    rs = torch.empty(n, dtype=torch.float32, device=W.device)
+    if n == 0:  # empty row shard: contributes zero column sums
+        return cs, rs
+    with torch.cuda.device(W.device):
+        _lib.check(_lib.lib().lcb_ria_sums(_ptr(W), _wdt(W), _ptr(cs), _ptr(rs), n, k, _stream(W.device)), "lcb_ria_sums")
+    return cs, rs
+
+
+def ria_metric(W, colsum, rowsum, scaler_row, alpha):
+    _need_cuda(W, colsum, rowsum, scaler_row)
+    n, k = W.shape
+    m = torch.empty((n, k), dtype=torch.float32, device=W.device)
+    if n == 0:
+        return m
+    scaler_row = scaler_row.to(torch.float32).contiguous()
+    with torch.cuda.device(W.device):
+        _lib.check(_lib.lib().lcb_ria_metric(_ptr(W), _wdt(W), _ptr(colsum), _ptr(rowsum), _ptr(scaler_row), _ptr(m), n, k,
+                                             float(alpha), _stream(W.device)), "lcb_ria_metric")
+    return m
+
+
+def mask_le(scores, thresh):
+    """scores <= thresh[0] (ref: the `<=` of ria/core.py:125, magnitude/core.py:42)."""
+    _need_cuda(scores, thresh)
+    mask = torch.empty(scores.shape, dtype=torch.uint8, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.check(_lib.lib().lcb_mask_le(_ptr(scores) if scores.numel() else None, _ptr(thresh),
+                                          _ptr(mask) if scores.numel() else None, scores.numel(), _stream(scores.device)),
+                   "lcb_mask_le")
+    return mask.bool()
 
 
 def apply_mask(W, mask):

@@ -9,8 +9,9 @@ The reference is single-device; these are the two natural shardings of its layer
     act-order permutation and per-row / per-group parameters (ref: gptq/core.py:226-265 touches rows
     only through W[:, cols]); `gather_rows` all-gathers the updated rows so every rank holds the full
     layer for the next calibration forward.  Statistics that span rows are reduced explicitly:
-    NVFP's per-matrix amax (ref: nvfp_quant.py:87) with `allreduce_max_`, SparseGPT's per-block
-    threshold and the RIA / magnitude global thresholds need the gathered scores (not sharded here).
+    NVFP's per-matrix amax (ref: nvfp_quant.py:87) with `allreduce_max_`; SparseGPT's per-block threshold
+    and the RIA / magnitude global thresholds with an exact distributed radix select (`select_kth_sharded`:
+    4 all-reduces of 256 counters, no gather of the scores); RIA's column sums with one all-reduce of [K].
 
 Only collectives and index arithmetic live here (they work with NCCL on CUDA tensors and with gloo on
 CPU tensors, which is how tests/test_parallel_cpu.py covers the N > 1 logic without a GPU); every
@@ -95,3 +96,71 @@ def gather_rows(local_rows, n_rows, group=None):
     out = torch.empty((w * per, k), dtype=local_rows.dtype, device=local_rows.device)
     dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
     return out[:n_rows]
+
+
+# ------------------------------------------------------------------ global thresholds over row shards
+def select_kth_sharded(scores_local, kth, group=None, backend=None):
+    """Exact k-th smallest (0-based) of fp32 scores spread over the ranks, without gathering them: MSB-first
+    radix select, per pass the local 256-bin histograms are summed with one all-reduce and every rank takes the
+    same branch (ref semantics: `sort(flatten)[kth]` of ria/core.py:124, magnitude/core.py:41).
+    Returns a [1] fp32 tensor, identical on every rank.  `backend` provides select_state / select_init /
+    select_hist / select_scan (default: llm_compressor_b200.ops, i.e. the CUDA kernels)."""
+    if backend is None:
+        from . import ops as backend
+    r, w = world()
+    state, hist = backend.select_state(scores_local.device)
+    thresh = torch.zeros(1, dtype=torch.float32, device=scores_local.device)
+    backend.select_init(state, kth)
+    flat = scores_local.reshape(-1)
+    for p in range(4):
+        backend.select_hist(state, flat, p)
+        if w > 1:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        backend.select_scan(state, p, thresh)
+    return thresh
+
+
+def _total(n_local, device, group=None):
+    r, w = world()
+    if w == 1:
+        return int(n_local)
+    t = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t.item())
+
+
+def mask_magnitude_sharded(W_local, ratio, group=None, backend=None):
+    """magnitude mask of a row-sharded weight (ref: magnitude/core.py:38-43): global threshold, local rows."""
+    if backend is None:
+        from . import ops as backend
+    numel = _total(W_local.numel(), W_local.device, group)
+    scores = backend.metric_magnitude(W_local)
+    kth = min(int(numel * ratio), numel - 1)
+    return backend.mask_le(scores, select_kth_sharded(scores, kth, group, backend))
+
+
+def mask_ria_sharded(W_local, scaler_row, ratio, alpha, group=None, backend=None):
+    """RIA mask of a row-sharded weight (ref: ria/core.py:118-126): column sums all-reduced in fp32 before the
+    rounding to W's dtype, row sums local, global threshold by `select_kth_sharded`."""
+    if backend is None:
+        from . import ops as backend
+    r, w = world()
+    numel = _total(W_local.numel(), W_local.device, group)
+    colsum, rowsum = backend.ria_sums(W_local)
+    if w > 1:
+        dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
+    scores = backend.ria_metric(W_local, colsum, rowsum, scaler_row, alpha)
+    kth = min(int(numel * ratio), numel - 1)
+    return backend.mask_le(scores, select_kth_sharded(scores, kth, group, backend))
+
+
+def sparsegpt_update_sharded(W_local, U, sparsity, block=128, group=None):
+    """SparseGPT block loop on this rank's rows with the exact global per-block threshold
+    (ref: sparsegpt/core.py:201-203; the histogram all-reduce runs inside the loop, 4 per block)."""
+    from . import ops
+    r, w = world()
+    if w == 1:
+        return ops.sparsegpt_update(W_local, U, sparsity, block)
+    n_total = _total(W_local.shape[0], W_local.device, group)
+    return ops.sparsegpt_update(W_local, U, sparsity, block, n_total=n_total,
+                                reduce=lambda hist: dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group))

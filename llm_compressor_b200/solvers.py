@@ -13,7 +13,7 @@ arithmetic stage runs in liblcb200.so through llm_compressor_b200.ops.
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, parallel
 
 
 def _is_conv1d(layer):
@@ -207,8 +207,10 @@ class Wrapper:
         _accumulate(self, x[0].detach())
 
 
-def prune_weight(layer, device, sparsity_ratio, block_size=128, percdamp=0.01):
-    """ref: pruning/sparsegpt/core.py:160-228"""
+def prune_weight(layer, device, sparsity_ratio, block_size=128, percdamp=0.01, shard_rows=False):
+    """ref: pruning/sparsegpt/core.py:160-228.  `shard_rows=True` under torch.distributed (one process per GPU):
+    every rank factors the (all-reduced) Hessian, solves its slice of the output rows with the exact global
+    per-block threshold (parallel.sparsegpt_update_sharded) and the rows are all-gathered."""
     W = layer.module.weight.data.clone()
     W = W.float().contiguous()
     H = finalize_hessian(layer)
@@ -217,7 +219,12 @@ def prune_weight(layer, device, sparsity_ratio, block_size=128, percdamp=0.01):
     W.masked_fill_(dead.unsqueeze(0), 0)
     U = ops.chol_inv_upper(H, perm=None, percdamp=percdamp)
     del H
-    ops.sparsegpt_update(W, U, sparsity_ratio, block=block_size)
+    if shard_rows and parallel.world()[1] > 1:
+        n_rows = W.shape[0]
+        part = parallel.sparsegpt_update_sharded(W[parallel.row_shard(n_rows)].contiguous(), U, sparsity_ratio, block_size)
+        W = parallel.gather_rows(part, n_rows)
+    else:
+        ops.sparsegpt_update(W, U, sparsity_ratio, block=block_size)
     layer.module.weight.data = W.reshape(layer.module.weight.shape).to(layer.module.weight.data.dtype)
 
 

@@ -101,6 +101,92 @@ def _ragged_case(rank, world):
     return bool(torch.equal(got, full))
 
 
+class _NumpyPhases:
+    """CPU stand-in for the phase kernels of csrc/masks.cu (lcb_select_* / lcb_metric_* / lcb_ria_* / lcb_mask_le),
+    so that the collective protocol of parallel.py can be exercised under gloo without a GPU.  TEST CODE ONLY."""
+
+    @staticmethod
+    def _keys(v):  # order-preserving uint32 keys of fp32 values (NaN last), like f2key
+        b = np.ascontiguousarray(v, np.float32).view(np.uint32)
+        return np.where(b >> 31, ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+    def select_state(self, device):
+        st = torch.zeros(4 + 256, dtype=torch.int32)
+        return st, st[4:]
+
+    def select_init(self, st, kth):
+        st.zero_()
+        self.prefix, self.krem = 0, int(kth)
+
+    def select_hist(self, st, scores, p):
+        k = self._keys(scores.numpy())
+        shift = 24 - 8 * p
+        himask = 0 if p == 0 else (0xFFFFFFFF << (shift + 8)) & 0xFFFFFFFF
+        sel = (k & np.uint32(himask)) == np.uint32(self.prefix & himask)
+        st[4:] += torch.from_numpy(np.bincount((k[sel] >> np.uint32(shift)) & np.uint32(0xFF), minlength=256).astype(np.int32))
+
+    def select_scan(self, st, p, thresh):
+        h = st[4:].numpy().astype(np.int64)
+        cum = np.cumsum(h)
+        b = int(np.searchsorted(cum, self.krem, side="right"))
+        b = min(b, 255)
+        self.krem -= int(cum[b - 1]) if b > 0 else 0
+        self.prefix |= b << (24 - 8 * p)
+        st[4:] = 0
+        if p == 3:
+            key = np.uint32(self.prefix)
+            bits = key & np.uint32(0x7FFFFFFF) if key >> 31 else ~key
+            thresh[0] = float(np.array([bits], np.uint32).view(np.float32)[0])
+
+    def metric_magnitude(self, W):
+        return W.float().abs()
+
+    def ria_sums(self, W):
+        a = W.float().abs()
+        return a.sum(0), a.sum(1).to(W.dtype).float()
+
+    def ria_metric(self, W, colsum, rowsum, srow, alpha):
+        a = W.abs()
+        base = a / colsum.to(W.dtype)[None, :] + a / rowsum.to(W.dtype)[:, None]     # W-dtype ops, one rounding each
+        return base.float() * torch.sqrt(srow.float())[None, :] ** alpha
+
+    def mask_le(self, scores, thresh):
+        return scores <= thresh[0]
+
+
+def _threshold_case(rank, world):
+    from llm_compressor_b200 import parallel
+    orc, X, W = _inputs()
+    be = _NumpyPhases()
+    Wt = torch.from_numpy(W).to(torch.bfloat16)
+    N = W.shape[0]
+    rows = parallel.row_shard(N)
+    srow = torch.from_numpy((X.astype(np.float32) ** 2).sum((0, 1)) / X.shape[0])
+    out = {}
+    # exact global k-th of sharded scores == sort(all)[kth]
+    scores = torch.from_numpy(np.abs(W)).float()
+    for kth in (0, 1, 5000, W.size // 2, W.size - 1):
+        th = parallel.select_kth_sharded(scores[rows].contiguous(), kth, backend=be)
+        out["kth%d" % kth] = bool(float(th) == float(np.sort(np.abs(W).reshape(-1))[kth]))
+    m = parallel.mask_magnitude_sharded(Wt[rows].contiguous(), 0.5, backend=be)
+    full, _ = orc.mask_magnitude(W, 0.5)
+    out["magnitude"] = bool(np.array_equal(m.numpy(), full[rows]))
+    m = parallel.mask_ria_sharded(Wt[rows].contiguous(), srow, 0.5, 0.5, backend=be)
+    full, _ = orc.mask_ria(W, srow.numpy(), 0.5, 0.5, orc.BF16)
+    out["ria_agree"] = float((m.numpy() == full[rows]).mean())
+    return out
+
+
+def test_row_sharded_global_thresholds_world2_and_3():
+    """Distributed radix select (4 histogram all-reduces) gives the exact global order statistic; the magnitude mask
+    of row shards equals the oracle's unsharded mask; RIA agrees up to the bf16 rounding of the re-associated column sums."""
+    for world in (2, 3):
+        for r in _run("_threshold_case", world):
+            assert all(v for k, v in r.items() if k.startswith("kth")), r
+            assert r["magnitude"], r
+            assert r["ria_agree"] > 0.999, r
+
+
 def test_sample_sharded_hessian_allreduce_matches_running_mean():
     res = _run("_hessian_case", 2)
     assert res[0]["n_tot"] == res[1]["n_tot"] == 5

@@ -344,3 +344,77 @@ def test_stacked_solve_equals_per_linear(gemm_mode):
     solvers.update_weights_shared(lins, DEV, fac)
     for a, l in zip(sep, lins):
         assert torch.equal(a, l.weight.data)
+
+
+# ------------------------------------------------------------------ row-sharded thresholds
+def _two_shard_kth(ops, parts, kth):
+    """lcb_select_* phases with the all-reduce of the two 'ranks' done by hand on one GPU."""
+    states = [ops.select_state(DEV) for _ in parts]
+    th = [torch.zeros(1, device=DEV) for _ in parts]
+    for st, _ in states:
+        ops.select_init(st, kth)
+    for p in range(4):
+        for (st, _), sc in zip(states, parts):
+            ops.select_hist(st, sc.reshape(-1), p)
+        total = sum(h for _, h in states)
+        for (st, h), t in zip(states, th):
+            h.copy_(total)
+            ops.select_scan(st, p, t)
+    assert all(torch.equal(th[0], t) for t in th)
+    return th[0]
+
+
+@pytest.mark.parametrize("N,K,split", [(512, 3072, 256), (300, 1000, 7), (64, 128, 64)])
+def test_phase_api_row_shards_equal_unsharded_masks(N, K, split):
+    ops = _ops()
+    g = torch.Generator().manual_seed(N + K)
+    W = (0.02 * torch.randn(N, K, generator=g)).to(torch.bfloat16).to(DEV)
+    s = (torch.rand(K, generator=g) * 4 + 0.01).to(DEV)
+    shards = [W[:split].contiguous(), W[split:].contiguous()]
+    for ratio in (0.5, 0.3):
+        kth = min(int(N * K * ratio), N * K - 1)
+        # magnitude: bit-exact
+        scores = [ops.metric_magnitude(w) for w in shards]
+        th = _two_shard_kth(ops, scores, kth)
+        got = torch.cat([ops.mask_le(sc, th) for sc in scores], 0)
+        assert torch.equal(got, ops.mask_magnitude(W, ratio))
+        assert float(th) == float(np.sort(np.abs(W.float().cpu().numpy()).reshape(-1))[kth])
+        # RIA: column sums re-associated (partial sums per shard) -> identical unless a bf16 rounding boundary moves
+        sums = [ops.ria_sums(w) for w in shards]
+        col = sums[0][0] + sums[1][0]
+        scores = [ops.ria_metric(w, col, rs, s, 0.5) for w, (_, rs) in zip(shards, sums)]
+        th = _two_shard_kth(ops, scores, kth)
+        got = torch.cat([ops.mask_le(sc, th) for sc in scores], 0)
+        agree = float((got == ops.mask_ria(W, s, ratio, 0.5)).float().mean())
+        assert agree > 0.9995, agree
+
+
+def test_sparsegpt_sharded_entry_world1_is_identical():
+    """lcb_sparsegpt_update_sharded with an identity reduce and n_total == n must reproduce lcb_sparsegpt_update."""
+    ops = _ops()
+    N, K = 256, 512
+    g = torch.Generator().manual_seed(5)
+    W = (0.02 * torch.randn(N, K, generator=g)).to(DEV)
+    X = torch.randn(2048, K, generator=g).to(DEV)
+    H = (X.T @ X) / 1024
+    U = ops.chol_inv_upper(H, percdamp=0.01)
+    a = ops.sparsegpt_update(W.clone(), U, 0.5)
+    calls = []
+    b = ops.sparsegpt_update(W.clone(), U, 0.5, n_total=N, reduce=lambda h: calls.append(int(h.sum())))
+    assert torch.equal(a, b)
+    assert len(calls) == 4 * (K // 128) and calls[0] == N * 128
+    with pytest.raises(RuntimeError):
+        ops.sparsegpt_update(W.clone(), U, 0.5, n_total=N, reduce=lambda h: (_ for _ in ()).throw(RuntimeError("boom")))
+
+
+def test_multi_gpu_sharded_pruning_script():
+    """2-GPU NCCL run of tests/mgpu_sharded.py (row-sharded SparseGPT / RIA / magnitude == unsharded); needs 2 GPUs."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "mgpu_sharded.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "mgpu sharded ok" in r.stdout
