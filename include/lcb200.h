@@ -45,6 +45,7 @@ extern "C" {
 /* storage / arithmetic dtype of a tensor: every primitive op rounds to this type, like torch */
 #define LCB_F32 0
 #define LCB_BF16 1
+#define LCB_F64 2 /* lcb_hadamard_rows only */
 
 /* quantizer families (ref: quantization/quant.py:36-63) */
 #define LCB_Q_INT 0  /* ref: quantizers/int_quant.py  */
@@ -252,6 +253,19 @@ int lcb_ria_metric(const void* W, int dtype, const float* colsum, const float* r
 int lcb_mask_le(const float* metric, const float* thresh, uint8_t* mask, int64_t numel, void* stream);
 /* W[mask] = 0 in place */
 int lcb_apply_mask(void* W, int dtype, const uint8_t* mask, int64_t numel, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Randomised Hadamard rotation (ref: spinquant/hadamard_utils.py:88-111 matmul_hadU,
+ * rotation_utils.py:40-45 random_hadamard_matrix, :57-113 rotate_*, hadamard_utils.py:135-172
+ * apply_exact_had_to_linear).  For every row of x [rows, n] (contiguous):
+ *     y = T(signs .* x) / divisor,   T = (H_K (x) I_L)(I_K (x) H_L),  n = K * L,  L = 2^m
+ * i.e. x @ (diag(signs) * matmul_hadU(I)) computed as a fast Walsh-Hadamard transform instead of the reference's
+ * dense fp64 GEMM.  hadk_bits: HOST array of K words, bit a of word a' set <=> H_K[a'][a] == -1 (K == 1: null);
+ * signs: device [n] of +-1 or null; divisor: float32(sqrt(n)) for the reference's normalisation;
+ * acc64 != 0 accumulates in fp64 (reference precision), else fp32.  x / y dtypes: LCB_F32 / LCB_BF16 / LCB_F64;
+ * in place (x == y) is allowed.  Column transforms (R^T @ W) are row transforms of the transpose. */
+int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype_out, int64_t rows, int64_t n, const float* signs,
+                      const uint64_t* hadk_bits, int K, double divisor, int acc64, void* stream);
 
 #ifdef __cplusplus
 }

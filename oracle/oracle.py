@@ -389,3 +389,45 @@ def sparsegpt_prune(W, H, sparsity, block_size=128, percdamp=0.01, out_dtype_bf1
         if i2 < K:
             W[:, i2:] -= E1 @ Hinv[i1:i2, i2:]
     return bf16_round(W) if out_dtype_bf16 else W
+
+
+# ----------------------------------------------------------------------------- Hadamard rotation
+def _hadk_table(K):
+    """The reference's fixed K x K Hadamard block (hadamard_utils.py get_had<K>), read from the golden fixture that
+    oracle/gen_golden_hadamard.py extracted from the reference itself."""
+    z = np.load(os.path.join(os.path.dirname(_HERE), "tests", "golden", "hadamard.npz"))
+    neg = np.unpackbits(z["had%d" % K])[: K * K].reshape(K, K).astype(bool)
+    return np.where(neg, -1.0, 1.0)
+
+
+def get_hadk(n):
+    """ref: hadamard_utils.py:17-85 (same precedence; only the sizes present in the fixture)."""
+    for K in (172, 156, 140, 108, 60, 52, 36, 28, 44, 40, 20, 12):
+        if n % K == 0:
+            return _hadk_table(K), K
+    return None, 1
+
+
+def matmul_hadU(X, transpose=False, signs=None):
+    """ref: hadamard_utils.py:88-111: radix-2 butterflies on the power-of-two part (adjacent pairs first), then the
+    K x K block across the leading index, then division by float32(sqrt(n)).  fp64 throughout.
+    signs: optional [n] of +-1 multiplied onto X first (= X @ diag(signs) @ matmul_hadU(I), rotation_utils.py:40-45)."""
+    X = np.asarray(X, np.float64)
+    n = X.shape[-1]
+    hadK, K = get_hadk(n)
+    if hadK is not None and transpose:
+        hadK = hadK.T
+    v = X.reshape(-1, n).copy()
+    if signs is not None:
+        v = v * np.asarray(signs, np.float64)[None, :]
+    B = v.shape[0]
+    cur = v.reshape(B, n, 1)
+    while cur.shape[1] > K:
+        cur = cur.reshape(B, cur.shape[1] // 2, 2, cur.shape[2])
+        nxt = np.empty_like(cur)
+        nxt[:, :, 0, :] = cur[:, :, 0, :] + cur[:, :, 1, :]
+        nxt[:, :, 1, :] = cur[:, :, 0, :] - cur[:, :, 1, :]
+        cur = nxt.reshape(B, cur.shape[1], -1)
+    if K > 1:
+        cur = hadK.reshape(1, K, K) @ cur
+    return cur.reshape(X.shape) / np.float64(np.sqrt(np.float32(n)))
