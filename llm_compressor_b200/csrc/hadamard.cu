@@ -14,6 +14,7 @@
 //   * accumulation in fp64 (default: results round to the same bf16 / fp32 values as the reference's fp64 GEMM
 //     up to ~1e-16 relative) or fp32.
 #include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 
@@ -31,7 +32,10 @@ struct HadArgs {
   int64_t rows;
   int n, m, K, rpc;
   int dt_in, dt_out;
+  int raw_bytes;  // tiled kernel: size of the raw staging area in front of the work buffer
+  int sgn_off;    // tiled kernel: byte offset of the packed sign words
   double divisor;  // the reference divides by float32(sqrt(n)) (hadamard_utils.py:111)
+  double rcp;      // 1 / divisor
   unsigned long long hk[HAD_MAXK];  // bit a of hk[a'] set  <=>  H_K[a'][a] == -1
 };
 
@@ -187,6 +191,271 @@ __global__ void __launch_bounds__(HAD_THREADS) hadamard_rows_kernel(const __grid
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Tiled kernel (m >= 5, bf16 / fp32 input, K in {1, 12, 40}): all global traffic is 16-byte vectors and the inner
+// loops are (nearly) one instruction per add.  The tile (rpc whole rows, one contiguous chunk) is copied raw into
+// shared memory with the sign vector XOR-ed into the sign bits on the way (signs packed to a bit mask once per CTA);
+// the stages then run in an order chosen for the memory system, not the reference's -- the factors of T act on
+// different index bits and commute (with bf16 inputs every fp64 partial sum is exact, so the order does not change a
+// single bit; fp32 accumulation moves within its rounding error):
+//   H_K stage first (raw tile -> work buffer; the K strided values of a column in registers, signs of H_K folded at
+//   compile time from the Paley construction; H_40 = H_2 (x) H_20 as one butterfly + two H_20), then the radix-2
+//   stages from the highest bit down in register-blocked passes of up to 5 bits (b0 >= 5: the padded address is
+//   linear in the register index), and the lowest 5 bits last so that every thread ends with 32 CONTIGUOUS outputs.
+//   Work-buffer index i lives at i + (i >> 5): every access pattern above (32 consecutive indices per warp, or lane g
+//   at 32 g + j) hits 32 distinct banks.
+__device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }  // one pad word per 32: see the bank analysis in DESIGN.md 3.7
+
+constexpr int chi_c(int a, int q) {  // Legendre symbol of a mod q (q prime)
+  a %= q;
+  if (a < 0) a += q;
+  if (a == 0) return 0;
+  long long r = 1, b = a;
+  for (int e = (q - 1) / 2; e > 0; e >>= 1) {
+    if (e & 1) r = (r * b) % q;
+    b = (b * b) % q;
+  }
+  return r == 1 ? 1 : -1;
+}
+// row mask (bit c set <=> entry (r, c) == -1) of the Paley-I matrix of order K = q + 1 the reference tabulates as
+// had12 / had20 (hadamard_utils.py; generated the same way in llm_compressor_b200/hadamard.py and checked against
+// the reference's tables by tests/test_hadamard.py)
+constexpr unsigned long long paley1_row_mask(int K, int r) {
+  unsigned long long m = 0;
+  for (int c = 0; c < K; ++c) {
+    bool neg = false;
+    if (r == 0) neg = c > 0;
+    else if (c == 0 || c == r) neg = false;
+    else neg = chi_c(c - r, K - 1) == 1;  // entry = -chi(c - r)
+    if (neg) m |= 1ull << c;
+  }
+  return m;
+}
+
+template <typename Acc, int KB, int R>
+__device__ __forceinline__ Acc paley_dot(const Acc (&v)[KB]) {
+  constexpr unsigned long long M = paley1_row_mask(KB, R);
+  Acc acc = ((M & 1ull) ? -v[0] : v[0]);
+#pragma unroll
+  for (int c = 1; c < KB; ++c) acc = ((M >> c) & 1ull) ? acc - v[c] : acc + v[c];
+  return acc;
+}
+template <typename Acc, int KB, int... Rs>
+__device__ __forceinline__ void paley_store(const Acc (&v)[KB], Acc* sm, int sbase, int m, std::integer_sequence<int, Rs...>) {
+  ((sm[pad32(sbase + (Rs << m))] = paley_dot<Acc, KB, Rs>(v)), ...);
+}
+
+template <typename Acc, typename TIn>
+__device__ __forceinline__ Acc raw_at(const unsigned char* raw, int idx) {
+  if constexpr (sizeof(TIn) == 2) return (Acc)__uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(raw)[idx] << 16);
+  else return (Acc) reinterpret_cast<const float*>(raw)[idx];
+}
+
+template <typename Acc, int N>
+__device__ __forceinline__ void butterfly_n(Acc (&v)[N]) {
+#pragma unroll
+  for (int h = 1; h < N; h <<= 1) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if ((j & h) == 0) {
+        const Acc p = v[j], q = v[j | h];
+        v[j] = p + q;
+        v[j | h] = p - q;
+      }
+    }
+  }
+}
+
+// scale (multiply by the reciprocal: its 2^-53 / 2^-24 error is far below the output rounding; fp64 output divides
+// like the reference), convert and store 16 contiguous outputs
+template <typename Acc>
+__device__ __forceinline__ void store16_out(void* y, int dt, int64_t e0, const Acc (&v)[16], double divisor, double rcpd) {
+  if (dt == LCB_BF16) {
+    const Acc rcp = (Acc)rcpd;
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat16 lo = __float2bfloat16_rn((float)(v[2 * i] * rcp));      // torch: double -> float -> bf16
+      const __nv_bfloat16 hi = __float2bfloat16_rn((float)(v[2 * i + 1] * rcp));
+      w[i] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+    }
+    uint4* p = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + e0);
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else if (dt == LCB_F32) {
+    const Acc rcp = (Acc)rcpd;
+    float4* p = reinterpret_cast<float4*>(static_cast<float*>(y) + e0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      p[i] = make_float4((float)(v[4 * i] * rcp), (float)(v[4 * i + 1] * rcp), (float)(v[4 * i + 2] * rcp),
+                         (float)(v[4 * i + 3] * rcp));
+  } else {
+    double2* p = reinterpret_cast<double2*>(static_cast<double*>(y) + e0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = make_double2((double)v[2 * i] / divisor, (double)v[2 * i + 1] / divisor);
+  }
+}
+
+// radix-2 stages on bits [b0, b0 + R), b0 >= 5: N = 2^R values per thread at a constant padded stride
+template <typename Acc, typename TIn, int R, bool SRC_RAW>
+__device__ __forceinline__ void mid_bits(const HadArgs& a, const unsigned char* raw, Acc* sm, int nr, int b0) {
+  constexpr int N = 1 << R;
+  const int groups = (nr * a.n) >> R;
+  const int lomask = (1 << b0) - 1;
+  const int step = 1 << b0, pstep = step + (step >> 5);
+  for (int g = threadIdx.x; g < groups; g += HAD_THREADS) {
+    const int base = ((g >> b0) << (b0 + R)) | (g & lomask);
+    Acc* p = sm + pad32(base);
+    Acc v[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if constexpr (SRC_RAW) v[j] = raw_at<Acc, TIn>(raw, base + j * step);
+      else v[j] = p[j * pstep];
+    }
+    butterfly_n<Acc, N>(v);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j * pstep] = v[j];
+  }
+}
+
+// the lowest 5 bits: 32 contiguous values per thread, straight to global memory
+template <typename Acc, typename TIn, bool SRC_RAW>
+__device__ __forceinline__ void low_bits_out(const HadArgs& a, const unsigned char* raw, const Acc* sm, int64_t row0, int nr) {
+  const int groups = (nr * a.n) >> 5;
+  for (int g = threadIdx.x; g < groups; g += HAD_THREADS) {
+    Acc v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if constexpr (SRC_RAW) v[j] = raw_at<Acc, TIn>(raw, 32 * g + j);
+      else v[j] = sm[33 * g + j];  // pad32(32 g + j): lane g, value j -> bank (g + j) % 32
+    }
+    butterfly_n<Acc, 32>(v);
+    Acc lo[16], hi[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { lo[j] = v[j]; hi[j] = v[16 + j]; }
+    const int64_t e0 = row0 * (int64_t)a.n + 32 * g;
+    store16_out<Acc>(a.y, a.dt_out, e0, lo, a.divisor, a.rcp);
+    store16_out<Acc>(a.y, a.dt_out, e0 + 16, hi, a.divisor, a.rcp);
+  }
+}
+
+// H_K across the leading index (stride L = 2^m), raw tile -> work buffer
+template <typename Acc, typename TIn, int KT>
+__device__ __forceinline__ void hadk_first(const HadArgs& a, const unsigned char* raw, Acc* sm, int nr) {
+  const int L = 1 << a.m;
+  for (int q = threadIdx.x; q < nr * L; q += HAD_THREADS) {
+    const int row = q >> a.m, b = q & (L - 1);
+    const int sbase = row * a.n + b;
+    if constexpr (KT == 12) {
+      Acc v[12];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) v[c] = raw_at<Acc, TIn>(raw, sbase + (c << a.m));
+      paley_store<Acc, 12>(v, sm, sbase, a.m, std::make_integer_sequence<int, 12>{});
+    } else if constexpr (KT == 40) {
+      Acc v0[20], v1[20];
+#pragma unroll
+      for (int c = 0; c < 20; ++c) {
+        const Acc p = raw_at<Acc, TIn>(raw, sbase + (c << a.m)), r = raw_at<Acc, TIn>(raw, sbase + ((c + 20) << a.m));
+        v0[c] = p + r;
+        v1[c] = p - r;
+      }
+      paley_store<Acc, 20>(v0, sm, sbase, a.m, std::make_integer_sequence<int, 20>{});
+      paley_store<Acc, 20>(v1, sm, sbase + (20 << a.m), a.m, std::make_integer_sequence<int, 20>{});
+    }
+  }
+}
+
+template <typename Acc, typename TIn, int KT>
+__global__ void __launch_bounds__(HAD_THREADS, sizeof(Acc) == 4 ? 4 : 2) hadamard_tile_kernel(const __grid_constant__ HadArgs a) {
+  extern __shared__ __align__(16) unsigned char had_smem[];
+  unsigned char* raw = had_smem;
+  Acc* sm = reinterpret_cast<Acc*>(had_smem + a.raw_bytes);
+  uint32_t* sgn = reinterpret_cast<uint32_t*>(had_smem + a.sgn_off);  // n / 32 words, bit set <=> sign < 0
+  constexpr int EPV = 16 / (int)sizeof(TIn);                          // elements per 16-byte vector
+  if (a.signs != nullptr) {
+    for (int i = threadIdx.x; i < a.n; i += HAD_THREADS) {  // n % 32 == 0 is not guaranteed: n % 16 == 0 is
+      const unsigned bal = __ballot_sync(__activemask(), a.signs[i] < 0.0f);
+      if ((threadIdx.x & 31) == 0) sgn[i >> 5] = bal;
+    }
+  }
+  __syncthreads();
+  for (int64_t row0 = (int64_t)blockIdx.x * a.rpc; row0 < a.rows; row0 += (int64_t)gridDim.x * a.rpc) {
+    const int nr = (int)min((int64_t)a.rpc, a.rows - row0);
+    {  // stage the raw tile (one contiguous chunk, 16-byte vectors) with the signs applied to the sign bits
+      const uint4* src = reinterpret_cast<const uint4*>(static_cast<const TIn*>(a.x) + row0 * (int64_t)a.n);
+      uint4* dst = reinterpret_cast<uint4*>(raw);
+      const int nvec = (nr * a.n) / EPV;
+      for (int i = threadIdx.x; i < nvec; i += HAD_THREADS) {
+        uint4 t = __ldg(src + i);
+        if (a.signs != nullptr) {
+          const int e = (i * EPV) % a.n;
+          const uint32_t bits = sgn[e >> 5] >> (e & 31);
+          if constexpr (EPV == 8) {
+            t.x ^= ((bits & 1u) << 15) | ((bits & 2u) << 30);
+            t.y ^= ((bits & 4u) << 13) | ((bits & 8u) << 28);
+            t.z ^= ((bits & 16u) << 11) | ((bits & 32u) << 26);
+            t.w ^= ((bits & 64u) << 9) | ((bits & 128u) << 24);
+          } else {
+            t.x ^= (bits & 1u) << 31;
+            t.y ^= (bits & 2u) << 30;
+            t.z ^= (bits & 4u) << 29;
+            t.w ^= (bits & 8u) << 28;
+          }
+        }
+        dst[i] = t;
+      }
+    }
+    __syncthreads();
+    bool from_raw = true;
+    if constexpr (KT > 1) {
+      hadk_first<Acc, TIn, KT>(a, raw, sm, nr);
+      __syncthreads();
+      from_raw = false;
+    }
+    int top = a.m;  // bits [5, top) are still to do
+    while (top > 5) {
+      const int hi = top - 5;
+      int r = hi % 5;
+      if (r == 0) r = 5;
+      if (hi > 5 && hi < 10) r = (hi + 1) / 2;  // 6..9 -> two balanced passes
+      const int b0 = top - r;
+#define LCB_HAD_PASS(RR)                                                        \
+  case RR:                                                                      \
+    if (from_raw) mid_bits<Acc, TIn, RR, true>(a, raw, sm, nr, b0);             \
+    else mid_bits<Acc, TIn, RR, false>(a, raw, sm, nr, b0);                     \
+    break;
+      switch (r) {
+        LCB_HAD_PASS(1) LCB_HAD_PASS(2) LCB_HAD_PASS(3) LCB_HAD_PASS(4) LCB_HAD_PASS(5)
+      }
+#undef LCB_HAD_PASS
+      __syncthreads();
+      from_raw = false;
+      top = b0;
+    }
+    if (from_raw) low_bits_out<Acc, TIn, true>(a, raw, sm, row0, nr);
+    else low_bits_out<Acc, TIn, false>(a, raw, sm, row0, nr);
+    __syncthreads();  // the next tile overwrites raw / sm
+  }
+}
+
+template <typename Acc, typename TIn, int KT>
+int launch_tile(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
+  LCB_CUDA(cudaFuncSetAttribute(hadamard_tile_kernel<Acc, TIn, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hadamard_tile_kernel<Acc, TIn, KT><<<grid, HAD_THREADS, smem, st>>>(a);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+template <typename Acc, typename TIn>
+int launch_tile_k(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
+  switch (a.K) {
+    case 1: return launch_tile<Acc, TIn, 1>(a, grid, smem, st);
+    case 12: return launch_tile<Acc, TIn, 12>(a, grid, smem, st);
+    default: return launch_tile<Acc, TIn, 40>(a, grid, smem, st);
+  }
+}
+
 template <typename Acc, int KT>
 int launch_had(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
   LCB_CUDA(cudaFuncSetAttribute(hadamard_rows_kernel<Acc, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -211,6 +480,19 @@ int launch_had_k(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
 
 using namespace lcb;
 
+// The tiled kernel folds the reference's had12 / had20 sign patterns at compile time; a caller-supplied table that
+// differs (the transposed one of matmul_hadUt, or any other H_K) takes the generic kernel.
+static bool transpose_table(const uint64_t* bits, int K) {
+  if (K == 1) return false;
+  const int kb = K == 40 ? 20 : K;
+  for (int r = 0; r < K; ++r) {
+    unsigned long long want = paley1_row_mask(kb, r % kb);
+    if (K == 40) want = (r < 20) ? (want | (want << 20)) : (want | ((~want & 0xfffffull) << 20));
+    if (bits[r] != want) return true;
+  }
+  return false;
+}
+
 extern "C" int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype_out, int64_t rows, int64_t n,
                                  const float* signs, const uint64_t* hadk_bits, int K, double divisor, int acc64,
                                  void* stream) {
@@ -225,21 +507,46 @@ extern "C" int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype
   LCB_REQUIRE((1ll << m) == L, "lcb_hadamard_rows: n / K must be a power of two");
   if (rows == 0) return LCB_OK;
   const size_t esz = acc64 ? sizeof(double) : sizeof(float);
+  HadArgs a{};
+  a.x = x; a.y = y; a.signs = signs; a.rows = rows; a.n = (int)n; a.m = m; a.K = K;
+  a.dt_in = dtype_in; a.dt_out = dtype_out; a.divisor = divisor; a.rcp = 1.0 / divisor;
+  for (int i = 0; i < K && K > 1; ++i) a.hk[i] = hadk_bits[i];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t esz_in = dtype_in == LCB_BF16 ? 2 : (dtype_in == LCB_F32 ? 4 : 8);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (m >= 5 && aligned && dtype_in != LCB_F64 && (K == 1 || K == 12 || K == 40) && !transpose_table(hadk_bits, K)) {
+    // tiled kernel: raw tile + padded work buffer + sign words; aim at two resident CTAs per SM
+    const int64_t budget = 100 * 1024;
+    const int64_t per_row = (int64_t)n * esz_in + (int64_t)(n + (n >> 5)) * esz;
+    int64_t rpc = std::max<int64_t>(1, budget / per_row);
+    rpc = std::min<int64_t>(rpc, std::max<int64_t>(1, 8192 / n));
+    const int64_t tile = rpc * n;
+    const size_t raw_bytes = (size_t)((tile * esz_in + 15) / 16 * 16);
+    const size_t work_bytes = (size_t)((tile + (tile >> 5) + 16) * esz + 15) / 16 * 16;
+    const size_t smem = raw_bytes + work_bytes + (size_t)(n / 32 + 2) * 4;
+    if (smem <= 220 * 1024) {
+      a.rpc = (int)rpc;
+      a.raw_bytes = (int)raw_bytes;
+      a.sgn_off = (int)(raw_bytes + work_bytes);
+      const int64_t tiles = ceil_div(rows, rpc);
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
+      const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
+      if (dtype_in == LCB_BF16)
+        return acc64 ? launch_tile_k<double, __nv_bfloat16>(a, grid, smem, st) : launch_tile_k<float, __nv_bfloat16>(a, grid, smem, st);
+      return acc64 ? launch_tile_k<double, float>(a, grid, smem, st) : launch_tile_k<float, float>(a, grid, smem, st);
+    }
+  }
+  // generic kernel: any K * 2^m (m < 4, unaligned pointers, rows too long for raw + work tiles)
   const int64_t max_elems = (int64_t)(200 * 1024 / esz) * 16 / 17;
   if (n > max_elems) {
     set_error("lcb_hadamard_rows: n = %lld exceeds the shared-memory tile (%lld)", (long long)n, (long long)max_elems);
     return LCB_ERR_UNSUPPORTED;
   }
-  HadArgs a{};
-  a.x = x; a.y = y; a.signs = signs; a.rows = rows; a.n = (int)n; a.m = m; a.K = K;
   a.rpc = (int)std::max<int64_t>(1, 4096 / n);
-  a.dt_in = dtype_in; a.dt_out = dtype_out; a.divisor = divisor;
-  for (int i = 0; i < K && K > 1; ++i) a.hk[i] = hadk_bits[i];
   const int64_t tile = (int64_t)a.rpc * n;
   const size_t smem = (size_t)(tile + (tile >> 4) + 16) * esz;
   const int64_t tiles = ceil_div(rows, a.rpc);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   return acc64 ? launch_had_k<double>(a, grid, smem, st) : launch_had_k<float>(a, grid, smem, st);
 }
