@@ -215,10 +215,10 @@ def run_ours(args):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 X = acts[gi]
-                n = 0
-                for j in my_samples:  # one hook call per calibration sample, like the reference
-                    n = ops.hessian_accum_raw(H, X[j], n)
-                n = parallel.reduce_hessian_(H, n)  # raw partial sums over NVLink (no-op on 1 GPU)
+                acc = ops.HessianAccumulator(H, args.hessian_defer)
+                for j in my_samples:  # one hook call per calibration sample ([1, 2048, K]), like the reference
+                    acc.add(X[j])
+                n = parallel.reduce_hessian_(H, acc.flush())  # raw partial sums over NVLink (no-op on 1 GPU)
                 ops.hessian_finalize(H, 2.0 / n, True)
                 e1.record()
                 evs.append((e0, e1, 2.0 * SEQ_LEN * K * K * len(my_samples), K))
@@ -280,7 +280,7 @@ def run_ours(args):
     fact_ms = sum(a.elapsed_time(b) for a, b, _ in stage_evs)      # last step (rank 0's view)
     upd_ms = sum(b.elapsed_time(c) for _, b, c in stage_evs)
     hess_last_ms = sum(a.elapsed_time(b) for a, b, _, _ in evs[-len(stage_evs):]) if stage_evs else 0.0
-    n_hess_launch = len(evs) * len(my_samples)
+    n_hess_launch = len(evs) * ((len(my_samples) + args.hessian_defer - 1) // args.hessian_defer)
 
     e2e_steps = max(1, min(args.steps, 2))
     one_model(True)  # warm the pinned-memory / copy-stream path
@@ -309,7 +309,8 @@ def run_ours(args):
         "config": {"workload": "Llama-3.2-3B shapes (28 layers x 7 Linears), GPTQ int4-g[128]-rw act-order, "
                                "synthetic 128x2048-token bf16 activations per Linear input, random-init bf16 weights",
                    "calibration_forwards": "outside the path (north_star)", "layers": args.layers, "hessians_per_layer": 4,
-                   "hessian_form": "raw sums of the symmetric half per sample + one finalize (2/n, mirror) per Hessian",
+                   "hessian_form": "one hook call per sample; raw sums of the symmetric half, %d hook inputs per kernel launch "
+                                   "(by reference, no copy), one finalize (2/n, mirror) per Hessian" % args.hessian_defer,
                    "solve_form": "q/k/v and gate/up stacked into one [sum N, K] solve per shared Hessian",
                    "l2_note": "activation buffer 4.3 GB and Hessians 38-268 MB: inputs larger than L2",
                    "parallelism": "samples sharded + all-reduce(H), rows sharded + all-gather" if world > 1 else "single GPU"},
@@ -420,6 +421,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--no-fake-quant", action="store_true", help="skip the fake-quant bandwidth section")
+    ap.add_argument("--hessian-defer", type=int, default=2,
+                    help="hook inputs accumulated per Hessian kernel launch (solvers.HESSIAN_DEFER); 1 = one launch per call")
     ap.add_argument("--layers", type=int, default=N_LAYERS,
                     help="decoder layers per step (default: the full 28-layer model; smaller only for profiling runs, "
                          "the JSON line then says so in config.layers)")

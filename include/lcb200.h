@@ -129,6 +129,14 @@ size_t lcb_hessian_ws_bytes(int64_t tokens, int64_t k);
 int lcb_hessian_accum(float* H, float* dxxt, const void* x, const void* x_fp, int64_t tokens, int64_t k,
                       float alpha, float beta, int upper_only, void* ws, size_t ws_bytes, void* stream);
 /* H *= scale; with symmetric_from_upper: H[i][j] = H[j][i] = scale * H[min(i,j)][max(i,j)] */
+/* Raw-sum accumulation of up to 8 hook inputs in ONE launch:  H += alpha * sum_i X_i^T X_i  (every X_i [tokens, k] bf16,
+ * xs = HOST array of `count` device pointers).  Equivalent to `count` lcb_hessian_accum(beta = 1) calls; each tile keeps
+ * one tensor-core accumulation chain over all count * tokens tokens, so H crosses L2 / HBM once per launch instead of
+ * once per hook call (K = 8192: the computed half of H is 140 MB > L2) and the per-launch prologue / drain is shared.
+ * The chain is `count` times longer: the tensor core's truncating fp32 accumulation gives relF ~ 4e-6 at 8192 tokens
+ * (1.6e-6 at 2048), a nearly uniform scale the solvers are invariant to. */
+int lcb_hessian_accum_multi(float* H, const void* const* xs, int count, int64_t tokens, int64_t k, float alpha,
+                            int upper_only, void* stream);
 int lcb_hessian_finalize(float* H, int64_t k, float scale, int symmetric_from_upper, void* stream);
 /* ref: wanda/core.py:92-105, ria/core.py:94-107:  s = beta*s + alpha * sum_t X[t,:]^2 */
 int lcb_rownorm_accum(float* s, const void* x, int64_t tokens, int64_t k, float alpha, float beta, void* stream);

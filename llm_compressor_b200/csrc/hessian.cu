@@ -86,9 +86,15 @@ constexpr uint32_t make_idesc() {
          ((uint32_t)(BM >> 4) << 24);
 }
 
+constexpr int MAX_SAMPLES = 8;  // hook inputs accumulated by one launch (lcb_hessian_accum_multi)
+struct alignas(64) XMaps {
+  CUtensorMap m[MAX_SAMPLES];
+};
+
 struct HessArgs {
   int64_t k;       // channels
-  int64_t tokens;
+  int64_t tokens;  // per sample
+  int kb_per_sample;  // 64-token blocks per sample; kblocks = samples * kb_per_sample
   float alpha;
   int tiles_m, tiles_n;
   int num_tiles;   // computed tiles
@@ -110,7 +116,7 @@ __device__ __forceinline__ void tile_coords(const HessArgs& a, int tile, int& m0
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant__ XMaps maps_b,
                     const __grid_constant__ CUtensorMap map_h, const __grid_constant__ HessArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -130,8 +136,8 @@ hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps_a.m[0])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps_b.m[0])) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_h)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
@@ -159,14 +165,15 @@ hessian_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         int m0, n0;
         tile_coords(a, tile, m0, n0);
         for (int kb = kb0; kb < kb1; ++kb) {
+          const int smp = kb / a.kb_per_sample, kbl = kb - smp * a.kb_per_sample;  // hook input, token block inside it
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
 #pragma unroll
-          for (int h = 0; h < BM / BOX_C; ++h) tma_load_2d(&map_a, &full[stage], sa + h * BOX_BYTES, m0 + h * BOX_C, kb * BKT);
+          for (int h = 0; h < BM / BOX_C; ++h) tma_load_2d(&maps_a.m[smp], &full[stage], sa + h * BOX_BYTES, m0 + h * BOX_C, kbl * BKT);
 #pragma unroll
-          for (int h = 0; h < BN / BOX_C; ++h) tma_load_2d(&map_b, &full[stage], sb + h * BOX_BYTES, n0 + h * BOX_C, kb * BKT);
+          for (int h = 0; h < BN / BOX_C; ++h) tma_load_2d(&maps_b.m[smp], &full[stage], sb + h * BOX_BYTES, n0 + h * BOX_C, kbl * BKT);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         u += kb1 - kb0;
@@ -289,7 +296,7 @@ constexpr uint32_t make_idesc_pair() {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-hessian_umma_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant__ XMaps maps_b,
                          const __grid_constant__ CUtensorMap map_h, const __grid_constant__ HessArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -310,8 +317,8 @@ hessian_umma_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const int64_t u0 = units * cluster / nclusters, u1 = units * (cluster + 1) / nclusters;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps_a.m[0])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps_b.m[0])) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_h)) : "memory");
     for (int i = 0; i < P_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
@@ -339,6 +346,7 @@ hessian_umma_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         int m0, n0;
         tile_coords(a, tile, m0, n0, 2 * PM);
         for (int kb = kb0; kb < kb1; ++kb) {
+          const int smp = kb / a.kb_per_sample, kbl = kb - smp * a.kb_per_sample;
           mbar_wait(&empty[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * P_STAGE_BYTES);  // both CTAs' boxes land on the leader's barrier
           const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
@@ -346,10 +354,10 @@ hessian_umma_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           uint8_t* sb = smem_b + stage * PB_BYTES;
 #pragma unroll
           for (int h = 0; h < PM / BOX_C; ++h)
-            tma_load_2d_pair(&map_a, lead_full, sa + h * BOX_BYTES, m0 + (int)rank * PM + h * BOX_C, kb * BKT);
+            tma_load_2d_pair(&maps_a.m[smp], lead_full, sa + h * BOX_BYTES, m0 + (int)rank * PM + h * BOX_C, kbl * BKT);
 #pragma unroll
           for (int h = 0; h < BN / 2 / BOX_C; ++h)
-            tma_load_2d_pair(&map_b, lead_full, sb + h * BOX_BYTES, n0 + (int)rank * (BN / 2) + h * BOX_C, kb * BKT);
+            tma_load_2d_pair(&maps_b.m[smp], lead_full, sb + h * BOX_BYTES, n0 + (int)rank * (BN / 2) + h * BOX_C, kbl * BKT);
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
         u += kb1 - kb0;
@@ -560,14 +568,23 @@ int make_h_map(CUtensorMap* map, float* h, int64_t k) {
   return LCB_OK;
 }
 
-// out += alpha * A_src^T B_src over the tokens; upper_only: only tiles touching the upper triangle
-int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens, int64_t k, float alpha, int upper_only,
-               cudaStream_t st) {
-  CUtensorMap map_a, map_b, map_h;
-  int rc = make_x_map(&map_a, a_src, tokens, k);
-  if (rc != LCB_OK) return rc;
-  rc = make_x_map(&map_b, b_src, tokens, k);
-  if (rc != LCB_OK) return rc;
+// out += alpha * sum_s A_s^T B_s over the tokens of `count` hook inputs (each [tokens, k]); upper_only: only tiles
+// touching the upper triangle.  One launch, one fp32 accumulation chain per tile over all count * tokens tokens.
+int launch_xtx_multi(float* out, const void* const* a_src, const void* const* b_src, int count, int64_t tokens, int64_t k,
+                     float alpha, int upper_only, cudaStream_t st) {
+  XMaps maps_a, maps_b;
+  CUtensorMap map_h;
+  int rc;
+  for (int i = 0; i < MAX_SAMPLES; ++i) {
+    if (i >= count) {  // unused slots repeat sample 0 (never dereferenced)
+      maps_a.m[i] = maps_a.m[0];
+      maps_b.m[i] = maps_b.m[0];
+      continue;
+    }
+    if ((rc = make_x_map(&maps_a.m[i], a_src[i], tokens, k)) != LCB_OK) return rc;
+    if (b_src[i] == a_src[i]) maps_b.m[i] = maps_a.m[i];
+    else if ((rc = make_x_map(&maps_b.m[i], b_src[i], tokens, k)) != LCB_OK) return rc;
+  }
   rc = make_h_map(&map_h, out, k);
   if (rc != LCB_OK) return rc;
   HessArgs a{};
@@ -587,7 +604,8 @@ int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens,
   }
   a.row_start[a.tiles_m] = (int16_t)acc;
   a.num_tiles = acc;
-  a.kblocks = (int)ceil_div(tokens, BKT);
+  a.kb_per_sample = (int)ceil_div(tokens, BKT);
+  a.kblocks = count * a.kb_per_sample;
   const int64_t units = (int64_t)a.num_tiles * a.kblocks;
   if (pair) {
     LCB_CUDA(cudaFuncSetAttribute(hessian_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
@@ -606,7 +624,7 @@ int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
-    LCB_CUDA(cudaLaunchKernelEx(&cfg, hessian_umma_pair_kernel, map_a, map_b, map_h, a));
+    LCB_CUDA(cudaLaunchKernelEx(&cfg, hessian_umma_pair_kernel, maps_a, maps_b, map_h, a));
     return LCB_OK;
   }
   LCB_CUDA(cudaFuncSetAttribute(hessian_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -614,9 +632,14 @@ int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens,
   int grid = sm_count();
   const int64_t cap = units / 8 > 0 ? units / 8 : 1;
   if (grid > cap) grid = (int)cap;
-  hessian_umma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_h, a);
+  hessian_umma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps_a, maps_b, map_h, a);
   LCB_LAUNCH_CHECK();
   return LCB_OK;
+}
+
+int launch_xtx(float* out, const void* a_src, const void* b_src, int64_t tokens, int64_t k, float alpha, int upper_only,
+               cudaStream_t st) {
+  return launch_xtx_multi(out, &a_src, &b_src, 1, tokens, k, alpha, upper_only, st);
 }
 
 int scale_inplace(float* p, int64_t n, float s, cudaStream_t st) {
@@ -634,6 +657,17 @@ int scale_inplace(float* p, int64_t n, float s, cudaStream_t st) {
 using namespace lcb;
 
 extern "C" size_t lcb_hessian_ws_bytes(int64_t tokens, int64_t k) { return (size_t)(tokens * k) * 2 * 2 + 512; }
+
+extern "C" int lcb_hessian_accum_multi(float* H, const void* const* xs, int count, int64_t tokens, int64_t k, float alpha,
+                                       int upper_only, void* stream) {
+  LCB_REQUIRE(H != nullptr && xs != nullptr && count >= 1 && count <= MAX_SAMPLES, "lcb_hessian_accum_multi: bad arguments");
+  LCB_REQUIRE(tokens > 0 && k > 0 && k % 8 == 0, "lcb_hessian_accum_multi: need tokens > 0 and k a positive multiple of 8");
+  LCB_REQUIRE((reinterpret_cast<uintptr_t>(H) & 15) == 0, "lcb_hessian_accum_multi: H must be 16-byte aligned");
+  for (int i = 0; i < count; ++i)
+    LCB_REQUIRE(xs[i] != nullptr && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0,
+                "lcb_hessian_accum_multi: every x must be a 16-byte aligned device pointer");
+  return launch_xtx_multi(H, xs, xs, count, tokens, k, alpha, upper_only, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int lcb_hessian_accum(float* H, float* dxxt, const void* x, const void* x_fp, int64_t tokens, int64_t k,
                                  float alpha, float beta, int upper_only, void* ws, size_t ws_bytes, void* stream) {

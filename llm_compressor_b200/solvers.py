@@ -26,19 +26,33 @@ def _is_conv1d(layer):
 #         reference's H (gptq/core.py:113-119 telescopes to (2/n) * sum_j X_j^T X_j).
 # "exact": every hook call leaves H equal to the reference's running mean (beta = n/(n+1), alpha = 2/(n+1)).
 HESSIAN_MODE = "lazy"
+# lazy mode: hook inputs accumulated per kernel launch (ops.HessianAccumulator keeps references to the deferred inputs
+# until the launch -- they must not be modified in place meanwhile); 1 = one launch per hook call
+HESSIAN_DEFER = 2
 
 
 def _accumulate(holder, x, dxxt=None, x_fp=None):
     if HESSIAN_MODE == "exact":
         holder.nsamples = ops.hessian_accum(holder.H, x, holder.nsamples, dxxt=dxxt, x_fp=x_fp)
-    else:
+    elif dxxt is not None or HESSIAN_DEFER <= 1:
         holder.nsamples = ops.hessian_accum_raw(holder.H, x, holder.nsamples, dxxt=dxxt, x_fp=x_fp)
+        holder._h_raw = True
+    else:
+        acc = getattr(holder, "_h_acc", None)
+        if acc is None or acc.H is not holder.H:
+            acc = holder._h_acc = ops.HessianAccumulator(holder.H, HESSIAN_DEFER)
+            acc.n = holder.nsamples
+        holder.nsamples = acc.add(x)
         holder._h_raw = True
 
 
 def finalize_hessian(holder):
     """Bring holder.H (and holder.dXXT) to the reference's running-mean value. Idempotent."""
     if getattr(holder, "_h_raw", False):
+        acc = getattr(holder, "_h_acc", None)
+        if acc is not None:
+            acc.flush()
+            del holder._h_acc
         scale = 2.0 / max(holder.nsamples, 1)
         ops.hessian_finalize(holder.H, scale, True)
         if getattr(holder, "dXXT", None) is not None:
