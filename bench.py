@@ -421,7 +421,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--no-fake-quant", action="store_true", help="skip the fake-quant bandwidth section")
-    ap.add_argument("--hessian-defer", type=int, default=2,
+    ap.add_argument("--hessian-defer", type=int, default=4,
                     help="hook inputs accumulated per Hessian kernel launch (solvers.HESSIAN_DEFER); 1 = one launch per call")
     ap.add_argument("--layers", type=int, default=N_LAYERS,
                     help="decoder layers per step (default: the full 28-layer model; smaller only for profiling runs, "

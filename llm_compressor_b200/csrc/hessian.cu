@@ -100,7 +100,43 @@ struct HessArgs {
   int num_tiles;   // computed tiles
   int kblocks;     // 64-token blocks per tile
   int upper_only;
+  int sched;       // 1: whole tiles in lock step + stream-K remainder, 0: stream-K over all units
   int16_t row_start[MAX_TILES_M + 1];  // prefix sum of computed tiles per tile row
+};
+
+// Work schedule of one CTA (or CTA pair): a sequence of segments (tile, [kb0, kb1)).
+//   1. whole tiles  cta, cta + G, cta + 2 G, ...  (G = CTAs / pairs in the grid), each over ALL token blocks: every CTA
+//      sweeps the token blocks 0 .. kblocks-1 in step with the others, so at any moment the whole grid reads the same
+//      few token blocks of X -- X streams through L2 once even when several deferred hook inputs (4 x 33 MB at K = 8192)
+//      no longer fit it, and the tiles in flight are neighbours in the tile list (shared row slices);
+//   2. the num_tiles % G left-over tiles, cut evenly over the grid stream-K style (partial tiles need no fix-up: every
+//      contribution is an L2 reduce-add).  `sched` = 0 keeps the plain stream-K split of all units (round-1 v1 schedule).
+struct WorkIter {
+  int whole, cta, G, kblocks, base_tile, i;
+  int64_t u, r1;
+  __device__ __forceinline__ WorkIter(const HessArgs& a, int cta_, int G_) {
+    cta = cta_; G = G_; kblocks = a.kblocks; i = 0;
+    whole = a.sched ? a.num_tiles / G : 0;
+    base_tile = whole * G;
+    const int64_t rem = (int64_t)(a.num_tiles - base_tile) * kblocks;
+    u = rem * cta / G;
+    r1 = rem * (cta + 1) / G;
+  }
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (i < whole) {
+      tile = cta + i * G; kb0 = 0; kb1 = kblocks; ++i;
+      return true;
+    }
+    if (u < r1) {
+      const int t = (int)(u / kblocks);
+      kb0 = (int)(u - (int64_t)t * kblocks);
+      kb1 = (int)min((int64_t)kblocks, kb0 + (r1 - u));
+      tile = base_tile + t;
+      u += kb1 - kb0;
+      return true;
+    }
+    return false;
+  }
 };
 
 // linear computed-tile index -> (m0, n0) for bm x BN tiles
@@ -131,9 +167,7 @@ hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // stream-K: this CTA owns the work units [u0, u1) of the (tile, token block) space
-  const int64_t units = (int64_t)a.num_tiles * a.kblocks;
-  const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+  const int sched_cta = (int)blockIdx.x, sched_n = (int)gridDim.x;  // see WorkIter
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps_a.m[0])) : "memory");
@@ -158,10 +192,8 @@ hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t u = u0; u < u1;) {
-        const int tile = (int)(u / a.kblocks);
-        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
-        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+      int tile, kb0, kb1;
+      for (WorkIter it(a, sched_cta, sched_n); it.next(tile, kb0, kb1);) {
         int m0, n0;
         tile_coords(a, tile, m0, n0);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -176,7 +208,6 @@ hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant_
           for (int h = 0; h < BN / BOX_C; ++h) tma_load_2d(&maps_b.m[smp], &full[stage], sb + h * BOX_BYTES, n0 + h * BOX_C, kbl * BKT);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
@@ -186,10 +217,8 @@ hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int64_t u = u0; u < u1; ++iter) {
-        const int tile = (int)(u / a.kblocks);
-        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
-        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+      int tile, kb0, kb1;
+      for (WorkIter it(a, sched_cta, sched_n); it.next(tile, kb0, kb1); ++iter) {
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -211,7 +240,6 @@ hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant_
           if (kb == kb1 - 1) umma_commit(&tfull[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        u += kb1 - kb0;
       }
     }
   } else {
@@ -219,10 +247,8 @@ hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     uint8_t* obuf = smem_out + (warp - 2) * 2 * OUT_BUF_BYTES;
     int iter = 0, nstore = 0;
-    for (int64_t u = u0; u < u1; ++iter) {
-      const int tile = (int)(u / a.kblocks);
-      const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
-      const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+    int tile, kb0, kb1;
+    for (WorkIter it(a, sched_cta, sched_n); it.next(tile, kb0, kb1); ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       int m0, n0;
@@ -262,7 +288,6 @@ hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant_
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
-      u += kb1 - kb0;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -313,8 +338,7 @@ hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-  const int64_t units = (int64_t)a.num_tiles * a.kblocks;
-  const int64_t u0 = units * cluster / nclusters, u1 = units * (cluster + 1) / nclusters;
+  const int sched_cta = (int)cluster, sched_n = (int)nclusters;  // see WorkIter
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps_a.m[0])) : "memory");
@@ -339,10 +363,8 @@ hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t u = u0; u < u1;) {
-        const int tile = (int)(u / a.kblocks);
-        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
-        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+      int tile, kb0, kb1;
+      for (WorkIter it(a, sched_cta, sched_n); it.next(tile, kb0, kb1);) {
         int m0, n0;
         tile_coords(a, tile, m0, n0, 2 * PM);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -360,7 +382,6 @@ hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_cons
             tma_load_2d_pair(&maps_b.m[smp], lead_full, sb + h * BOX_BYTES, n0 + (int)rank * (BN / 2) + h * BOX_C, kbl * BKT);
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
-        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
@@ -370,10 +391,8 @@ hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int64_t u = u0; u < u1; ++iter) {
-        const int tile = (int)(u / a.kblocks);
-        const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
-        const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+      int tile, kb0, kb1;
+      for (WorkIter it(a, sched_cta, sched_n); it.next(tile, kb0, kb1); ++iter) {
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -394,7 +413,6 @@ hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_cons
           if (kb == kb1 - 1) umma_commit_pair(&tfull[as], 3);
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
-        u += kb1 - kb0;
       }
     }
   } else {
@@ -402,10 +420,8 @@ hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_cons
     const int q = warp & 3;
     uint8_t* obuf = smem_out + (warp - 2) * 2 * OUT_BUF_BYTES;
     int iter = 0, nstore = 0;
-    for (int64_t u = u0; u < u1; ++iter) {
-      const int tile = (int)(u / a.kblocks);
-      const int kb0 = (int)(u - (int64_t)tile * a.kblocks);
-      const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+    int tile, kb0, kb1;
+    for (WorkIter it(a, sched_cta, sched_n); it.next(tile, kb0, kb1); ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       int m0, n0;
@@ -443,7 +459,6 @@ hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_cons
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));  // the leader's MMA warp waits for 8 warps
-      u += kb1 - kb0;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -531,6 +546,15 @@ __global__ void __launch_bounds__(256) rownorm_kernel(float* __restrict__ s, con
 }
 
 // [tokens, k] bf16 row-major -> 2D map, dim0 = channels (contiguous), dim1 = tokens, 64 x 64 boxes
+// LCB_HESSIAN_SCHED=0 selects the plain stream-K schedule (A/B measurements); default: lock-step whole tiles
+int hessian_sched_mode() {
+  static const int mode = [] {
+    const char* e = std::getenv("LCB_HESSIAN_SCHED");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  return mode;
+}
+
 int make_x_map(CUtensorMap* map, const void* x, int64_t tokens, int64_t k) {
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
@@ -589,6 +613,7 @@ int launch_xtx_multi(float* out, const void* const* a_src, const void* const* b_
   if (rc != LCB_OK) return rc;
   HessArgs a{};
   a.k = k; a.tokens = tokens; a.alpha = alpha; a.upper_only = upper_only;
+  a.sched = hessian_sched_mode();
   const bool pair = hessian_pair_mode(k);
   const int bm = pair ? 2 * PM : BM;
   a.tiles_m = (int)ceil_div(k, bm); a.tiles_n = (int)ceil_div(k, BN);

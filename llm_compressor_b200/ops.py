@@ -80,12 +80,13 @@ class HessianAccumulator:
     accumulation chain over all of them.  No copy is made: the accumulator keeps a REFERENCE to each deferred input
     until it is flushed, so the caller must not modify those tensors in place before `flush()` (hook inputs are
     intermediate activations that nothing writes to afterwards; use defer=1 if in doubt).
-    Measured on B200 (Llama-3.2-3B shapes, 128 x 2048 tokens): Hessian stage 0.70 s at defer=1, 0.62 s at 2, 0.62 s at 4,
-    0.69 s at 8 -- beyond 2 the stream-K schedule spreads the CTAs over all deferred inputs at once and X no longer stays
-    in L2 (K = 8192: 4 x 33 MB), so 2 is the default.
+    Measured on B200 (Llama-3.2-3B shapes, 128 x 2048 tokens, lock-step tile schedule of csrc/hessian.cu): Hessian stage
+    0.72 s at defer=1, 0.60 s at 2, 0.56 s at 4, 0.52 s at 8 (executed tensor rate 1.02 -> 1.40 PFLOP/s).  The price is the
+    chain length: the tensor core's fp32 accumulator truncates, relF(H) grows from ~5e-6 (2048 tokens) to ~2e-5 (8192) and
+    ~5e-5 (16384) at K = 8192; GPTQ's layer-output SQNR moves by < 0.001 dB (tests/test_solvers_gpu.py), default 4.
     `flush()` (called by solvers.finalize_hessian) launches whatever is pending and returns the sample count."""
 
-    def __init__(self, H, defer=2):
+    def __init__(self, H, defer=4):
         self.H, self.defer, self.n = H, max(1, min(int(defer), MAX_DEFER)), 0
         self._pending = []
 

@@ -28,7 +28,7 @@ def _is_conv1d(layer):
 HESSIAN_MODE = "lazy"
 # lazy mode: hook inputs accumulated per kernel launch (ops.HessianAccumulator keeps references to the deferred inputs
 # until the launch -- they must not be modified in place meanwhile); 1 = one launch per hook call
-HESSIAN_DEFER = 2
+HESSIAN_DEFER = 4
 
 
 def _accumulate(holder, x, dxxt=None, x_fp=None):
