@@ -275,6 +275,14 @@ int lcb_apply_mask(void* W, int dtype, const uint8_t* mask, int64_t numel, void*
 int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype_out, int64_t rows, int64_t n, const float* signs,
                       const uint64_t* hadk_bits, int K, double divisor, int acc64, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Packed export.  The reference stores only fake-quantised bf16 weights (ref: models/llama.py:210-230);
+ * its integer / fp4 codes are the intermediate `q` of fake_quantize (int_quant.py:210-212, utils.py:263-272), which
+ * lcb_qdq returns as one uint8 per element.  lcb_pack4 packs 4-bit codes two per byte (element 2i in the low nibble),
+ * lcb_unpack4 restores the uint8 codes (is_signed: sign-extend INT4 two's complement, else zero-extend fp4). */
+int lcb_pack4(const uint8_t* codes, uint8_t* packed, int64_t numel, void* stream);
+int lcb_unpack4(const uint8_t* packed, uint8_t* codes, int64_t numel, int is_signed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,6 +150,8 @@ _OPTIONAL = [
     ("lcb_ria_sums", [_vp, _i32, _vp, _vp, _i64, _i64, _vp], _i32),
     ("lcb_ria_metric", [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp], _i32),
     ("lcb_mask_le", [_vp, _vp, _vp, _i64, _vp], _i32),
+    ("lcb_pack4", [_vp, _vp, _i64, _vp], _i32),
+    ("lcb_unpack4", [_vp, _vp, _i64, _i32, _vp], _i32),
     ("lcb_hadamard_rows", [_vp, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _i32, _f64, _i32, _vp], _i32),
     ("lcb_set_gemm_mode", [_i32], _i32),
     ("lcb_tgemm_ws_bytes", [_i64, _i64, _i64], _sz),
