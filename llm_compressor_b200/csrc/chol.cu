@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, in
 // keeps L11 in shared memory and solves its own 128-row tile of the panel, L21 = A21 * L11^-T, with the same
 // 8-wide blocked steps (the 8 x 8 diagonal inverses come out of the factorisation).  The tile is written
 // back in place and as tf32 hi / lo planes (ld NB) for the SYRK GEMMs that follow.
-constexpr int LS = NB + 4;
+constexpr int LS = NB + 1;  // 8 rows apart = 8 banks apart (see the TRSM half of chol_panel_kernel)
 constexpr int PANEL_SMEM = (NB * LS + 2 * NB * PS + 16 * 64) * (int)sizeof(float);
 
 __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, int64_t j, int nb, int64_t m2,
@@ -326,90 +326,98 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, i
 #pragma unroll
     for (int c = 0; c < 8; ++c) Lsm[(ty * 8 + i) * LS + tx * 8 + c] = a[i][c];
 
-  // ---- my row tile of A21
+  // ---- my row tile of A21:  X = A21 L11^-T.  Rows are independent, so this half needs no block barrier: four
+  // adjacent lanes share a pair of rows, lane `qd` owns the 8-column panels qd, qd + 4, qd + 8, qd + 12 of both rows
+  // (interleaved: balanced trailing work).  Per 8-column step the owner multiplies its panel by the inverse of the
+  // 8 x 8 diagonal tile (from the factorisation), the 16 results go to the other three lanes by shuffle, and every lane
+  // updates its own panels to the right.  L11 is read from shared memory (row stride 129: the four panels a warp
+  // touches in one load sit 8 banks apart).
+  const int rp = tid >> 2, qd = tid & 3;
   const int64_t r0 = (int64_t)blockIdx.x * NB;  // first row of the tile inside the panel
   float* A21 = A + (j + nb + r0) * ld + j;
+  float x[2][4][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool ok = r0 + ty * 8 + i < m2;
-    const float* rp = A21 + (int64_t)(ty * 8 + i) * ld + tx * 8;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (ok) { v0 = *reinterpret_cast<const float4*>(rp); v1 = *reinterpret_cast<const float4*>(rp + 4); }
-    a[i][0] = v0.x; a[i][1] = v0.y; a[i][2] = v0.z; a[i][3] = v0.w;
-    a[i][4] = v1.x; a[i][5] = v1.y; a[i][6] = v1.z; a[i][7] = v1.w;
+  for (int rr = 0; rr < 2; ++rr) {
+    const bool ok = r0 + 2 * rp + rr < m2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* rpnt = A21 + (int64_t)(2 * rp + rr) * ld + 8 * (qd + 4 * k);
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (ok) { v0 = *reinterpret_cast<const float4*>(rpnt); v1 = *reinterpret_cast<const float4*>(rpnt + 4); }
+      x[rr][k][0] = v0.x; x[rr][k][1] = v0.y; x[rr][k][2] = v0.z; x[rr][k][3] = v0.w;
+      x[rr][k][4] = v1.x; x[rr][k][5] = v1.y; x[rr][k][6] = v1.z; x[rr][k][7] = v1.w;
+    }
   }
-  __syncthreads();  // Lsm complete; factor_block's last use of P0 is over
-#pragma unroll 1
+  __syncthreads();  // Lsm and dall complete
+#pragma unroll
   for (int p = 0; p < 16; ++p) {
-    float* P = (p & 1) ? P1 : P0;
-    if (tx == p) {  // X_ip = A_ip * L_pp^-T : new[i][c] = sum_{m <= c} a[i][m] * Dinv[c][m]
-      float dv[8][8];
+    const int owner = p & 3, slot = p >> 2;
+    if (qd == owner) {  // X_p = A_p * L_pp^-T : new[c] = sum_{m <= c} a[m] * Dinv[c][m]
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) dv[i][c] = dall[p][i * 8 + c];
-      float nw[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int rr = 0; rr < 2; ++rr) {
+        float nw[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float acc = 0.f;
 #pragma unroll
-          for (int m = 0; m <= c; ++m) acc = fmaf(a[i][m], dv[c][m], acc);
-          nw[i][c] = acc;
+          for (int m = 0; m <= c; ++m) acc = fmaf(x[rr][slot][m], dall[p][c * 8 + m], acc);
+          nw[c] = acc;
         }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+        for (int c = 0; c < 8; ++c) x[rr][slot][c] = nw[c];
+      }
+    }
+    float xp[2][8];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) xp[rr][c] = __shfl_sync(0xffffffffu, x[rr][slot][c], owner, 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int q = qd + 4 * k;
+      if (4 * k + 3 <= p) continue;  // compile-time: no lane owns a panel to the right in this slot
+      if (q > p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          a[i][c] = nw[i][c];
-          P[(ty * 8 + i) * PS + c] = nw[i][c];
+          const float* lrow = Lsm + (8 * q + c) * LS + 8 * p;
+          float a0 = x[0][k][c], a1 = x[1][k][c];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const float l = lrow[m];
+            a0 = fmaf(-xp[0][m], l, a0);
+            a1 = fmaf(-xp[1][m], l, a1);
+          }
+          x[0][k][c] = a0;
+          x[1][k][c] = a1;
         }
+      }
     }
-    __syncthreads();
-    if (tx > p) {  // A_i,tx -= X_ip * L_tx,p^T
-      float lr[8][8], lc[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          lr[i][m] = P[(ty * 8 + i) * PS + m];
-          lc[i][m] = Lsm[(tx * 8 + i) * LS + p * 8 + m];
-        }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float acc = a[i][c];
-#pragma unroll
-          for (int m = 0; m < 8; ++m) acc = fmaf(-lr[i][m], lc[c][m], acc);
-          a[i][c] = acc;
-        }
-    }
-    // the other P buffer is written next: no barrier needed here (it was last read two steps ago,
-    // before the barrier above)
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t rl = r0 + ty * 8 + i;
+  for (int rr = 0; rr < 2; ++rr) {
+    const int64_t rl = r0 + 2 * rp + rr;
     if (rl >= m2) continue;
-    float* rp = A21 + (int64_t)(ty * 8 + i) * ld + tx * 8;
-    *reinterpret_cast<float4*>(rp) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
-    *reinterpret_cast<float4*>(rp + 4) = make_float4(a[i][4], a[i][5], a[i][6], a[i][7]);
-    float h[8], l[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint32_t hb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a[i][c]));
-      h[c] = __uint_as_float(hb);
-      l[c] = __fsub_rn(a[i][c], h[c]);
+    for (int k = 0; k < 4; ++k) {
+      const int col = 8 * (qd + 4 * k);
+      float* rpnt = A21 + (int64_t)(2 * rp + rr) * ld + col;
+      *reinterpret_cast<float4*>(rpnt) = make_float4(x[rr][k][0], x[rr][k][1], x[rr][k][2], x[rr][k][3]);
+      *reinterpret_cast<float4*>(rpnt + 4) = make_float4(x[rr][k][4], x[rr][k][5], x[rr][k][6], x[rr][k][7]);
+      float h[8], l[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x[rr][k][c]));
+        h[c] = __uint_as_float(hb);
+        l[c] = __fsub_rn(x[rr][k][c], h[c]);
+      }
+      float* hp = panelH + rl * NB + col;
+      float* lp = panelL + rl * NB + col;
+      *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(hp + 4) = make_float4(h[4], h[5], h[6], h[7]);
+      *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<float4*>(lp + 4) = make_float4(l[4], l[5], l[6], l[7]);
     }
-    float* hp = panelH + rl * NB + tx * 8;
-    float* lp = panelL + rl * NB + tx * 8;
-    *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(hp + 4) = make_float4(h[4], h[5], h[6], h[7]);
-    *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]);
-    *reinterpret_cast<float4*>(lp + 4) = make_float4(l[4], l[5], l[6], l[7]);
   }
 }
 
