@@ -181,6 +181,109 @@ __device__ __forceinline__ void factor_block(float (&a)[8][8], float* P, float (
   }
 }
 
+// Variant for the panel kernel (tensor-core path), tuned for the latency of the 16-step chain:
+//   * the diagonal-tile thread only FACTORS its 8 x 8 tile (the inverse took more than half of that single-thread
+//     phase); the panel tiles below are solved by substitution against it; the 16 tile inverses the TRSM half of
+//     chol_panel_kernel wants are computed by the 16 diagonal threads in parallel at the end;
+//   * the column panel is exchanged as P[m][row] (8 x 128) and read with 128-bit loads: 32 instead of 128 shared loads
+//     per thread and step, ~4x fewer wavefronts (the row-major padded layout had 4-way conflicts on the column side).
+// Same outputs as factor_block up to rounding.  P: 8 * NB floats (16-byte aligned), D: 64 + 8 floats.
+__device__ __forceinline__ void factor_block_fast(float (&a)[8][8], float* P, float* D, float (*dall)[64], bool& bad,
+                                                  int ty, int tx) {
+#pragma unroll 1
+  for (int p = 0; p < 16; ++p) {
+    if (ty == p && tx == p) {
+      float rl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = a[j][j];
+        if (!(d > 0.0f)) bad = true;
+        float r = rsqrtf(d);
+        r = fmaf(r, fmaf(-0.5f * d * r, r, 0.5f), r);
+        rl[j] = r;
+        a[j][j] = d * r;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) a[i][j] *= r;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c)
+#pragma unroll
+          for (int i = c; i < 8; ++i) a[i][c] = fmaf(-a[i][j], a[c][j], a[i][c]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c > i) a[i][c] = 0.0f;
+          D[i * 8 + c] = a[i][c];
+        }
+        D[64 + i] = rl[i];
+      }
+    }
+    __syncthreads();
+    if (tx == p && ty >= p) {
+      if (ty > p) {  // L_ip = A_ip * L_pp^-T by substitution: x_c = (a_c - sum_{m < c} x_m l_cm) / l_cc, 8 rows in parallel
+        float l[8][8], r[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          r[c] = D[64 + c];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) l[c][m] = D[c * 8 + m];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float acc = a[i][c];
+#pragma unroll
+            for (int m = 0; m < c; ++m) acc = fmaf(-a[i][m], l[c][m], acc);
+            a[i][c] = acc * r[c];
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        *reinterpret_cast<float4*>(P + c * NB + ty * 8) = make_float4(a[0][c], a[1][c], a[2][c], a[3][c]);
+        *reinterpret_cast<float4*>(P + c * NB + ty * 8 + 4) = make_float4(a[4][c], a[5][c], a[6][c], a[7][c]);
+      }
+    }
+    __syncthreads();
+    if (ty > p && tx > p && tx <= ty) {  // trailing update of the lower tiles
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float4 r0 = *reinterpret_cast<const float4*>(P + m * NB + ty * 8), r1 = *reinterpret_cast<const float4*>(P + m * NB + ty * 8 + 4);
+        const float4 c0 = *reinterpret_cast<const float4*>(P + m * NB + tx * 8), c1 = *reinterpret_cast<const float4*>(P + m * NB + tx * 8 + 4);
+        const float lr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const float lc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[i][c] = fmaf(-lr[i], lc[c], a[i][c]);
+      }
+    }
+    // P and D are rewritten only after the next iteration's first barrier
+  }
+  if (ty == tx) {  // inverses of the 8 x 8 diagonal tiles, all 16 in parallel
+    float di[8][8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) di[i][jj] = 0.0f;
+      di[jj][jj] = __frcp_rn(a[jj][jj]);
+#pragma unroll
+      for (int i = jj + 1; i < 8; ++i) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int m = jj; m < i; ++m) sacc = fmaf(a[i][m], di[m][jj], sacc);
+        di[i][jj] = -sacc * __frcp_rn(a[i][i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dall[ty][i * 8 + c] = di[i][c];
+  }
+}
+
 // x = L^-1 for the factor held in `a` (dall from factor_block); x must enter as the identity tiles.
 // P: NB * PS floats, XP: 8 * (NB + 4) floats of scratch.
 __device__ __forceinline__ void invert_block(const float (&a)[8][8], float (&x)[8][8], float* P, float* XP,
@@ -311,7 +414,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, i
       a[i][c] = v;
     }
   bool bad = false;
-  factor_block(a, P0, dall, bad, ty, tx);
+  factor_block_fast(a, P0, P1, dall, bad, ty, tx);  // P0: [8][NB] column panel, P1: diagonal tile + pivots
   if (blockIdx.x == 0) {
     // L11 goes to a side buffer [NB x NB]: the other CTAs of this launch are still reading Ajj
     if (bad && status) atomicOr(status, LCB_ST_NOT_SPD);
@@ -349,74 +452,82 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, i
     }
   }
   __syncthreads();  // Lsm and dall complete
+  // The loops stay ROLLED (slot 0 always holds the panel being finished; finished panels are stored and the register
+  // panels shift down): fully unrolled this half was ~200 KB of SASS and ran out of the instruction cache.
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) {
+#pragma unroll 1
+    for (int o = 0; o < 4; ++o) {
+      const int p = 4 * s + o;
+      if (qd == o) {  // X_p = A_p * L_pp^-T : new[c] = sum_{m <= c} a[m] * Dinv[c][m]
 #pragma unroll
-  for (int p = 0; p < 16; ++p) {
-    const int owner = p & 3, slot = p >> 2;
-    if (qd == owner) {  // X_p = A_p * L_pp^-T : new[c] = sum_{m <= c} a[m] * Dinv[c][m]
+        for (int rr = 0; rr < 2; ++rr) {
+          float nw[8];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        float nw[8];
+          for (int c = 0; c < 8; ++c) {
+            float acc = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float acc = 0.f;
-#pragma unroll
-          for (int m = 0; m <= c; ++m) acc = fmaf(x[rr][slot][m], dall[p][c * 8 + m], acc);
-          nw[c] = acc;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) x[rr][slot][c] = nw[c];
-      }
-    }
-    float xp[2][8];
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) xp[rr][c] = __shfl_sync(0xffffffffu, x[rr][slot][c], owner, 4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int q = qd + 4 * k;
-      if (4 * k + 3 <= p) continue;  // compile-time: no lane owns a panel to the right in this slot
-      if (q > p) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float* lrow = Lsm + (8 * q + c) * LS + 8 * p;
-          float a0 = x[0][k][c], a1 = x[1][k][c];
-#pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const float l = lrow[m];
-            a0 = fmaf(-xp[0][m], l, a0);
-            a1 = fmaf(-xp[1][m], l, a1);
+            for (int m = 0; m <= c; ++m) acc = fmaf(x[rr][0][m], dall[p][c * 8 + m], acc);
+            nw[c] = acc;
           }
-          x[0][k][c] = a0;
-          x[1][k][c] = a1;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x[rr][0][c] = nw[c];
+        }
+      }
+      float xp[2][8];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xp[rr][c] = __shfl_sync(0xffffffffu, x[rr][0][c], o, 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // register panel k holds panel q = qd + 4 (s + k); it lies to the right of p iff k > 0 or qd > o
+        if (k < 4 - s && (k > 0 || qd > o)) {
+          const float* lbase = Lsm + (8 * (qd + 4 * (s + k))) * LS + 8 * p;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float* lrow = lbase + c * LS;
+            float a0 = x[0][k][c], a1 = x[1][k][c];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const float l = lrow[m];
+              a0 = fmaf(-xp[0][m], l, a0);
+              a1 = fmaf(-xp[1][m], l, a1);
+            }
+            x[0][k][c] = a0;
+            x[1][k][c] = a1;
+          }
         }
       }
     }
-  }
+    // panel qd + 4 s is final for both rows: store it (in place + tf32 hi / lo planes), shift the register panels
+    const int col = 8 * (qd + 4 * s);
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int64_t rl = r0 + 2 * rp + rr;
-    if (rl >= m2) continue;
+    for (int rr = 0; rr < 2; ++rr) {
+      const int64_t rl = r0 + 2 * rp + rr;
+      if (rl < m2) {
+        float* rpnt = A21 + (int64_t)(2 * rp + rr) * ld + col;
+        *reinterpret_cast<float4*>(rpnt) = make_float4(x[rr][0][0], x[rr][0][1], x[rr][0][2], x[rr][0][3]);
+        *reinterpret_cast<float4*>(rpnt + 4) = make_float4(x[rr][0][4], x[rr][0][5], x[rr][0][6], x[rr][0][7]);
+        float h[8], l[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int col = 8 * (qd + 4 * k);
-      float* rpnt = A21 + (int64_t)(2 * rp + rr) * ld + col;
-      *reinterpret_cast<float4*>(rpnt) = make_float4(x[rr][k][0], x[rr][k][1], x[rr][k][2], x[rr][k][3]);
-      *reinterpret_cast<float4*>(rpnt + 4) = make_float4(x[rr][k][4], x[rr][k][5], x[rr][k][6], x[rr][k][7]);
-      float h[8], l[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x[rr][k][c]));
-        h[c] = __uint_as_float(hb);
-        l[c] = __fsub_rn(x[rr][k][c], h[c]);
+        for (int c = 0; c < 8; ++c) {
+          uint32_t hb;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x[rr][0][c]));
+          h[c] = __uint_as_float(hb);
+          l[c] = __fsub_rn(x[rr][0][c], h[c]);
+        }
+        float* hp = panelH + rl * NB + col;
+        float* lp = panelL + rl * NB + col;
+        *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(hp + 4) = make_float4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<float4*>(lp + 4) = make_float4(l[4], l[5], l[6], l[7]);
       }
-      float* hp = panelH + rl * NB + col;
-      float* lp = panelL + rl * NB + col;
-      *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(hp + 4) = make_float4(h[4], h[5], h[6], h[7]);
-      *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]);
-      *reinterpret_cast<float4*>(lp + 4) = make_float4(l[4], l[5], l[6], l[7]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[rr][k][c] = x[rr][k + 1][c];
     }
   }
 }
