@@ -68,9 +68,9 @@ __global__ void reverse_out_kernel(float* __restrict__ U, const float* __restric
   U[i * k + j] = (j >= i) ? Linv[(k - 1 - i) * k + (k - 1 - j)] : 0.0f;
 }
 
-__global__ void zero_strict_upper_kernel(float* A, int64_t k) {
+__global__ void zero_strict_upper_kernel(float* A, int64_t k, int64_t i0) {  // rows i0 .. i0 + gridDim.y - 1
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = blockIdx.y;
+  const int64_t i = i0 + blockIdx.y;
   if (j < k && j > i) A[i * k + j] = 0.0f;
 }
 
@@ -534,16 +534,17 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, i
 
 // Inverse of every 128 x 128 diagonal block of the factor, in place (base of the trtri recursion): one CTA
 // per block, all blocks in one launch.
-__global__ void __launch_bounds__(256) diag_inv_kernel(float* A, int64_t k, const float* Lblk_all) {
+__global__ void __launch_bounds__(256) diag_inv_kernel(float* A, int64_t k, const float* Lblk_all, int b0) {
   __shared__ float P[NB * PS];
   __shared__ float XP[8 * (NB + 4)];
   __shared__ float dall[16][64];
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
-  const int64_t j = (int64_t)blockIdx.x * NB;
+  const int64_t blk = (int64_t)b0 + blockIdx.x;
+  const int64_t j = blk * NB;
   const int nb = (int)min((int64_t)NB, k - j);
   float* Ajj = A + j * k + j;
-  const float* Lb = Lblk_all + (int64_t)blockIdx.x * NB * NB;  // factor block (identity padded) from chol_panel_kernel
+  const float* Lb = Lblk_all + blk * NB * NB;  // factor block (identity padded) from chol_panel_kernel
   float a[8][8], x[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -607,8 +608,9 @@ SideStreams* side_streams() {
   if (!ready[dev]) {
     SideStreams& c = cache[dev];
     bool ok = true;
-    for (int i = 0; i < 2; ++i) ok = ok && cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 3; ++i) ok = ok && cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c.evP, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c.evT, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2; ++i) {
       ok = ok && cudaEventCreateWithFlags(&c.evB[i], cudaEventDisableTiming) == cudaSuccess;
       ok = ok && cudaEventCreateWithFlags(&c.evS[i], cudaEventDisableTiming) == cudaSuccess;
@@ -678,6 +680,62 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   gather_reverse_damp_kernel<<<g2, 256, 0, st>>>(A, H, perm, k, damp, dsum);
   LCB_LAUNCH_CHECK();
 
+  // ---- one level of the recursive triangular inverse, in place, nodes [t_begin, t_end) of size 2 s:
+  //      [[A,0],[C,B]]^-1 = [[A^-1,0],[-B^-1 C A^-1, B^-1]]   (A^-1, B^-1 already in place)
+  auto trtri_nodes = [&](int64_t s, int64_t t_begin, int64_t t_end, cudaStream_t ts) -> int {
+    int r;
+    if (tg && s >= TRI_TG_MIN) {
+      // tensor cores, node by node:  T^T = A^-T C^T  and  C <- -B^-1 T  as two NT GEMMs on hi/lo planes
+      for (int64_t t0 = t_begin; t0 < t_end; ++t0) {
+        const int64_t base = t0 * 2 * s;
+        const int64_t sB = std::min<int64_t>(s, k - base - s);
+        if (sB <= 0) break;
+        float* Ainv = A + base * k + base;
+        float* Cblk = A + (base + s) * k + base;
+        float* Binv = A + (base + s) * k + (base + s);
+        float* ATh = T;                 // [s, s]   planes of Ainv^T (upper triangular)
+        float* ATl = ATh + s * s;
+        float* Ch = ATl + s * s;        // [sB, s]  planes of C
+        float* Cl = Ch + sB * s;
+        float* TT = Cl + sB * s;        // [s, sB]  T^T
+        float* TTh = TT + s * sB;
+        float* TTl = TTh + s * sB;
+        float* Bh = TTl + s * sB;       // [sB, sB] planes of Binv (lower triangular)
+        float* Bl = Bh + sB * sB;
+        if ((r = split_tf32(Ainv, k, (int)s, (int)s, ATh, ATl, s, 1, ts)) != LCB_OK) return r;
+        if ((r = split_tf32(Cblk, k, (int)sB, (int)s, Ch, Cl, s, 0, ts)) != LCB_OK) return r;
+        if ((r = split_tf32(Binv, k, (int)sB, (int)sB, Bh, Bl, sB, 0, ts)) != LCB_OK) return r;
+        r = tgemm_nt(ATh, ATl, s, Ch, Cl, s, TT, sB, (int)s, (int)sB, (int)s, 1.0f, TG_STORE | TG_A_UPPER, ts, TG_CHAIN);
+        if (r != LCB_OK) return r;
+        if ((r = split_tf32(TT, sB, (int)s, (int)sB, TTh, TTl, sB, 0, ts)) != LCB_OK) return r;
+        r = tgemm_nt(Bh, Bl, sB, TTh, TTl, sB, Cblk, k, (int)sB, (int)s, (int)sB, -1.0f, TG_STORE | TG_A_LOWER, ts, TG_CHAIN);
+        if (r != LCB_OK) return r;
+      }
+      return LCB_OK;
+    }
+    for (int64_t t0 = t_begin; t0 < t_end;) {
+      // batch consecutive nodes with the same (full) size; the ragged last node goes alone
+      const int64_t base = t0 * 2 * s;
+      const int64_t sB0 = std::min<int64_t>(s, k - base - s);
+      if (sB0 <= 0) break;
+      int64_t cnt = 1;
+      if (sB0 == s) {
+        while (t0 + cnt < t_end && (k - (t0 + cnt) * 2 * s - s) >= s) ++cnt;
+      }
+      float* Ainv = A + base * k + base;
+      float* Cblk = A + (base + s) * k + base;
+      float* Binv = A + (base + s) * k + (base + s);
+      GemmArgs g1 = gemm_args(Cblk, k, Ainv, k, T, s, (int)sB0, (int)s, (int)s, 1.0f, 0.0f, 0, GEMM_B_LOWER);
+      g1.batch = (int)cnt; g1.strideA = g1.strideB = 2 * s * (k + 1); g1.strideC = s * s;
+      if ((r = sgemm(g1, ts)) != LCB_OK) return r;
+      GemmArgs g2a = gemm_args(Binv, k, T, s, Cblk, k, (int)sB0, (int)s, (int)sB0, -1.0f, 0.0f, 0, GEMM_A_LOWER);
+      g2a.batch = (int)cnt; g2a.strideA = g2a.strideC = 2 * s * (k + 1); g2a.strideB = s * s;
+      if ((r = sgemm(g2a, ts)) != LCB_OK) return r;
+      t0 += cnt;
+    }
+    return LCB_OK;
+  };
+
   int rc;
   if (!tg) {
     // ---- blocked right-looking Cholesky (lower) of A, exact fp32
@@ -714,6 +772,7 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
     auto fail = [&](int code) {  // nothing may outlive the workspace
       cudaStreamSynchronize(ss->s[0]);
       cudaStreamSynchronize(ss->s[1]);
+      cudaStreamSynchronize(ss->s[2]);
       return code;
     };
     int64_t q = 0;  // panel counter
@@ -755,6 +814,25 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
           if (rc != LCB_OK) return fail(rc);
         }
       }
+      // ---- the square [0, j1) x [0, j1) of the factor is final: its part of the triangular inverse runs NOW on side
+      // stream 2, underneath the rest of the (latency-bound) panel chain, instead of after it.  Nodes are emitted in
+      // post-order: everything inside this super-panel (diagonal blocks, levels 128 and 256), then every larger node
+      // that ends exactly here; what is left for after the chain are the ragged nodes at the matrix edge.
+      {
+        cudaStream_t ts = ss->s[2];
+        LCB_CUDA(cudaEventRecord(ss->evT, st));
+        LCB_CUDA(cudaStreamWaitEvent(ts, ss->evT, 0));
+        const int64_t rows = j1 - j0;
+        dim3 gz((unsigned)ceil_div(k, 256), (unsigned)rows);
+        zero_strict_upper_kernel<<<gz, 256, 0, ts>>>(A, k, j0);
+        LCB_LAUNCH_CHECK();
+        diag_inv_kernel<<<(unsigned)ceil_div(rows, NB), 256, 0, ts>>>(A, k, dinv_all, (int)(j0 / NB));
+        LCB_LAUNCH_CHECK();
+        for (int64_t s = NB; 2 * s <= SW; s *= 2)
+          if ((rc = trtri_nodes(s, j0 / (2 * s), ceil_div(j1, 2 * s), ts)) != LCB_OK) return fail(rc);
+        for (int64_t s = SW; s < k; s *= 2)
+          if (j1 % (2 * s) == 0 && (rc = trtri_nodes(s, j1 / (2 * s) - 1, j1 / (2 * s), ts)) != LCB_OK) return fail(rc);
+      }
       const int64_t m3 = k - j1;
       if (m3 > 0) {
         // the strip is final once the last B of this super-panel is done
@@ -784,70 +862,22 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
       if (evB_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[e], 0));
       if (evS_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evS[e], 0));
     }
+    // ragged nodes at the matrix edge (size 2 s does not divide k), children first; then join stream 2
+    for (int64_t s = SW; s < k; s *= 2) {
+      const int64_t t_last = k / (2 * s);
+      if (k % (2 * s) != 0 && k - t_last * 2 * s > s && (rc = trtri_nodes(s, t_last, t_last + 1, ss->s[2])) != LCB_OK)
+        return fail(rc);
+    }
+    LCB_CUDA(cudaEventRecord(ss->evT, ss->s[2]));
+    LCB_CUDA(cudaStreamWaitEvent(st, ss->evT, 0));
   }
-  zero_strict_upper_kernel<<<g2, 256, 0, st>>>(A, k);
-  LCB_LAUNCH_CHECK();
-  if (tg) {
-    diag_inv_kernel<<<(unsigned)nblk, 256, 0, st>>>(A, k, dinv_all);  // all diagonal blocks inverted in one launch
-  } else {
+  if (!tg) {
+    zero_strict_upper_kernel<<<g2, 256, 0, st>>>(A, k, 0);
+    LCB_LAUNCH_CHECK();
     put_diag_blocks_kernel<<<(unsigned)nblk, 256, 0, st>>>(A, k, dinv_all);
-  }
-  LCB_LAUNCH_CHECK();
-
-  // ---- recursive triangular inverse, in place: [[A,0],[C,B]]^-1 = [[A^-1,0],[-B^-1 C A^-1, B^-1]]
-  for (int64_t s = NB; s < k; s *= 2) {
-    const int64_t nodes = ceil_div(k, 2 * s);
-    if (tg && s >= TRI_TG_MIN) {
-      // tensor cores, node by node:  T^T = A^-T C^T  and  C <- -B^-1 T  as two NT GEMMs on hi/lo planes
-      for (int64_t t0 = 0; t0 < nodes; ++t0) {
-        const int64_t base = t0 * 2 * s;
-        const int64_t sB = std::min<int64_t>(s, k - base - s);
-        if (sB <= 0) break;
-        float* Ainv = A + base * k + base;
-        float* Cblk = A + (base + s) * k + base;
-        float* Binv = A + (base + s) * k + (base + s);
-        float* ATh = T;                 // [s, s]   planes of Ainv^T (upper triangular)
-        float* ATl = ATh + s * s;
-        float* Ch = ATl + s * s;        // [sB, s]  planes of C
-        float* Cl = Ch + sB * s;
-        float* TT = Cl + sB * s;        // [s, sB]  T^T
-        float* TTh = TT + s * sB;
-        float* TTl = TTh + s * sB;
-        float* Bh = TTl + s * sB;       // [sB, sB] planes of Binv (lower triangular)
-        float* Bl = Bh + sB * sB;
-        if ((rc = split_tf32(Ainv, k, (int)s, (int)s, ATh, ATl, s, 1, st)) != LCB_OK) return rc;
-        if ((rc = split_tf32(Cblk, k, (int)sB, (int)s, Ch, Cl, s, 0, st)) != LCB_OK) return rc;
-        if ((rc = split_tf32(Binv, k, (int)sB, (int)sB, Bh, Bl, sB, 0, st)) != LCB_OK) return rc;
-        rc = tgemm_nt(ATh, ATl, s, Ch, Cl, s, TT, sB, (int)s, (int)sB, (int)s, 1.0f, TG_STORE | TG_A_UPPER, st, TG_CHAIN);
-        if (rc != LCB_OK) return rc;
-        if ((rc = split_tf32(TT, sB, (int)s, (int)sB, TTh, TTl, sB, 0, st)) != LCB_OK) return rc;
-        rc = tgemm_nt(Bh, Bl, sB, TTh, TTl, sB, Cblk, k, (int)sB, (int)s, (int)sB, -1.0f, TG_STORE | TG_A_LOWER, st, TG_CHAIN);
-        if (rc != LCB_OK) return rc;
-      }
-      continue;
-    }
-    for (int64_t t0 = 0; t0 < nodes;) {
-      // batch consecutive nodes with the same (full) size; the ragged last node goes alone
-      const int64_t base = t0 * 2 * s;
-      const int64_t sB0 = std::min<int64_t>(s, k - base - s);
-      if (sB0 <= 0) break;
-      int64_t cnt = 1;
-      if (sB0 == s) {
-        while (t0 + cnt < nodes && (k - (t0 + cnt) * 2 * s - s) >= s) ++cnt;
-      }
-      float* Ainv = A + base * k + base;
-      float* Cblk = A + (base + s) * k + base;
-      float* Binv = A + (base + s) * k + (base + s);
-      GemmArgs g1 = gemm_args(Cblk, k, Ainv, k, T, s, (int)sB0, (int)s, (int)s, 1.0f, 0.0f, 0, GEMM_B_LOWER);
-      g1.batch = (int)cnt; g1.strideA = g1.strideB = 2 * s * (k + 1); g1.strideC = s * s;
-      rc = sgemm(g1, st);
-      if (rc != LCB_OK) return rc;
-      GemmArgs g2a = gemm_args(Binv, k, T, s, Cblk, k, (int)sB0, (int)s, (int)sB0, -1.0f, 0.0f, 0, GEMM_A_LOWER);
-      g2a.batch = (int)cnt; g2a.strideA = g2a.strideC = 2 * s * (k + 1); g2a.strideB = s * s;
-      rc = sgemm(g2a, st);
-      if (rc != LCB_OK) return rc;
-      t0 += cnt;
-    }
+    LCB_LAUNCH_CHECK();
+    for (int64_t s = NB; s < k; s *= 2)
+      if ((rc = trtri_nodes(s, 0, ceil_div(k, 2 * s), st)) != LCB_OK) return rc;
   }
   reverse_out_kernel<<<g2, 256, 0, st>>>(U, A, k);
   LCB_LAUNCH_CHECK();

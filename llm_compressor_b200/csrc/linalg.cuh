@@ -66,8 +66,8 @@ int gemm_mode();
 // (Cholesky panels, GPTQ block steps) -- the update the next step needs stays on the caller's stream, the rest
 // runs underneath the following steps.  nullptr (and lcb_last_error set) when they cannot be created.
 struct SideStreams {
-  cudaStream_t s[2];
-  cudaEvent_t evP, evB[2], evS[2];
+  cudaStream_t s[3];  // 0: B(q) panel updates, 1: S_B(J) strip updates, 2: triangular inverse of finished blocks
+  cudaEvent_t evP, evB[2], evS[2], evT;
 };
 SideStreams* side_streams();
 
