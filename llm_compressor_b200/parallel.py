@@ -164,3 +164,11 @@ def sparsegpt_update_sharded(W_local, U, sparsity, block=128, group=None):
     n_total = _total(W_local.shape[0], W_local.device, group)
     return ops.sparsegpt_update(W_local, U, sparsity, block, n_total=n_total,
                                 reduce=lambda hist: dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group))
+
+
+def nvfp_quantize_rows_sharded(quantizer, W_local, group=None):
+    """NVFP fake-quant of this rank's rows with the per-MATRIX amax of the reference (nvfp_quant.py:87): local
+    lcb_nvfp_global_amax, all-reduce(MAX), lcb_qdq with nv_amax -- bit-identical to quantising the unsharded matrix."""
+    amax = quantizer.global_amax(W_local)
+    allreduce_max_(amax, group)
+    return quantizer(W_local, nv_amax=amax)

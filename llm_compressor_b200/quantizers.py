@@ -309,6 +309,33 @@ class NVFPQuantizer(MXQuantizer):
         self.register_buffer("s_max_norm", torch.tensor(s_max_norm))
 
 
+    def global_amax(self, x):
+        """Phase 1 alone (lcb_nvfp_global_amax): the [1] fp32 amax over the blocks of `x` (ref: nvfp_quant.py:87).  With
+        row-sharded weights all-reduce(MAX) it (parallel.allreduce_max_) and pass it to forward(x, nv_amax=...)."""
+        if not x.is_cuda:
+            raise _lib.LcbError("liblcb200 needs CUDA tensors (no CPU fallback); got device %s" % x.device)
+        x = x.contiguous()
+        self._resolve_group(x)
+        assert self.axes == -1, "global_amax: row-sharded use is along the last axis"
+        rows, cols = _prod(tuple(x.shape[:-1])), x.shape[-1]
+        out = torch.zeros(1, dtype=torch.float32, device=x.device)
+        cfg = self._cfg()
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().lcb_nvfp_global_amax(ctypes.byref(cfg), _dt(x), _ptr(x), 1, rows, cols, -1, self.group_size,
+                                                 _ptr(out), _stream(x.device))
+        _lib.check(rc, "lcb_nvfp_global_amax")
+        return out
+
+    def forward(self, x, **kwargs):
+        nv_amax = kwargs.pop("nv_amax", None)
+        if nv_amax is None:
+            return super().forward(x, **kwargs)
+        self._resolve_group(x)
+        out, _, _, _ = qdq_raw(self._cfg(self._mse()), x, self.axes, self.group_size, True, True, nv_amax=nv_amax,
+                               check_nan=self.check_nan)
+        return out
+
+
 class DummyQuantizer(nn.Module):  # ref: quantizers/dummy.py:9
     def __init__(self, is_profile=False, **kwargs):
         super().__init__()
