@@ -134,6 +134,33 @@ def fake_quant_bandwidth(lc, torch, dev, hbm_gbs):
     return out
 
 
+def rotation_bandwidth(torch, dev, hbm_gbs):
+    """randomised Hadamard rotation W @ R1 (lcb_hadamard_rows) on a [65536, n] bf16 tensor (larger than
+    L2), n = 3072 (Llama-3.2-3B hidden, K = 12) and 2560 (Gemma-3 / Qwen3 hidden, K = 40).  4 B / element (read + write)."""
+    from llm_compressor_b200 import hadamard as H
+    out = {}
+    for n in (3072, 2560):
+        g = torch.Generator(device=dev).manual_seed(n)
+        x = (0.02 * torch.randn(8 * 8192, n, generator=g, device=dev)).to(torch.bfloat16)
+        s = (torch.randint(0, 2, (n,), generator=g, device=dev) * 2 - 1).float()
+        y = torch.empty_like(x)
+        for acc64 in (True, False):
+            for _ in range(3):
+                H.hadamard_rows(x, s, acc64=acc64, out=y)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                H.hadamard_rows(x, s, acc64=acc64, out=y)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 10
+            gbs = x.numel() * 4 / ms / 1e6
+            out["n%d_%s" % (n, "fp64acc" if acc64 else "fp32acc")] = {"GBs": gbs, "frac_of_hbm_peak": gbs / hbm_gbs, "ms": ms}
+        del x, y
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -292,6 +319,7 @@ def run_ours(args):
         return
     peak_tf, hbm_gbs, src = peaks()
     fq = fake_quant_bandwidth(lc, torch, dev, hbm_gbs) if not args.no_fake_quant else None
+    rot = rotation_bandwidth(torch, dev, hbm_gbs) if not args.no_fake_quant else None
     achieved = hess_flops / (hess_ms_total * 1e-3) / 1e12
     executed = hess_exec / (hess_ms_total * 1e-3) / 1e12
     wbytes = sum(N * K * 2 for K, lins in GROUPS for _, N in lins) * args.layers
@@ -336,6 +364,7 @@ def run_ours(args):
                      "launches": n_hess_launch, "avg_launch_ms": hess_ms_total / max(n_hess_launch, 1),
                      "stage_share_of_step": hess_ms_total / ms},
         "fake_quant": fq,
+        "hadamard_rotation": rot,
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))
