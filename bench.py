@@ -229,7 +229,9 @@ def run_ours(args):
             if not from_host or layer >= args.layers:
                 return
             with torch.cuda.stream(copy_stream):
-                w = weights_host[layer][gi].to(dev, non_blocking=True)
+                wh = weights_host[layer][gi]
+                # rows are sharded over the ranks for the solve: each rank stages only its own rows
+                w = wh[parallel.row_shard(wh.shape[0])].to(dev, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             staged[(layer, gi)] = (w, ev)
@@ -254,17 +256,17 @@ def run_ours(args):
                 fac = solvers.factorize(H, WCFG["group_size"], actorder=True, percdamp=0.01)
                 e2.record()
                 del H
+                ntot = weights_dev[layer][gi].shape[0]
+                rows = parallel.row_shard(ntot)  # rows are independent given U: shard them over ranks
                 if from_host:
-                    w, ev = staged.pop((layer, gi))
+                    w, ev = staged.pop((layer, gi))   # this rank's rows only
                     cur.wait_event(ev)
                     w.record_stream(cur)
                 else:
-                    w = weights_dev[layer][gi]
-                ntot = w.shape[0]
-                rows = parallel.row_shard(ntot)  # rows are independent given U: shard them over ranks
+                    w = weights_dev[layer][gi][rows]
                 # the group's Linears as one stacked problem (solvers.update_weights_shared does this stacking
                 # for separate modules; here the weights are stored stacked)
-                lin = Lin(w[rows])
+                lin = Lin(w)
                 solvers.update_weight(lin, dev, block_size=128, percdamp=0.01, actorder=True, factor=fac)
                 e3 = torch.cuda.Event(enable_timing=True)
                 e3.record()
@@ -273,10 +275,11 @@ def run_ours(args):
                 if from_host:  # device -> pinned host buffer on the D2H stream, ordered after the solve by an event
                     done = torch.cuda.Event()
                     done.record(cur)
+                    mine = lin.weight.data  # every rank writes its own rows of the result to the host buffer
                     with torch.cuda.stream(d2h_stream):
                         d2h_stream.wait_event(done)
-                        out_host[layer][gi].copy_(out, non_blocking=True)
-                    out.record_stream(d2h_stream)
+                        out_host[layer][gi][rows].copy_(mine, non_blocking=True)
+                    mine.record_stream(d2h_stream)
         if from_host:
             cur.wait_stream(d2h_stream)  # the step ends when the last result has reached the host buffer
         return evs
@@ -352,7 +355,7 @@ def run_ours(args):
                    "parallelism": "samples sharded + all-reduce(H), rows sharded + all-gather" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_ms / 1e3 / e2e_steps, "unit": "s/model", "h2d_bytes_per_step": wbytes,
                 "d2h_bytes_per_step": wbytes,
-                "note": "weights in pinned host memory, H2D prefetched one group ahead on a copy stream, results "
+                "note": "weights in pinned host memory (each rank stages and returns its own row shard), H2D prefetched one group ahead on a copy stream, results "
                         "copied back to pinned host memory on a second copy stream (all inside the timed region); activations are produced on the device in the "
                         "reference flow too"},
         "gpu_launches": int(launches),
