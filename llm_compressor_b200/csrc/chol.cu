@@ -181,107 +181,201 @@ __device__ __forceinline__ void factor_block(float (&a)[8][8], float* P, float (
   }
 }
 
-// Variant for the panel kernel (tensor-core path), tuned for the latency of the 16-step chain:
-//   * the diagonal-tile thread only FACTORS its 8 x 8 tile (the inverse took more than half of that single-thread
-//     phase); the panel tiles below are solved by substitution against it; the 16 tile inverses the TRSM half of
-//     chol_panel_kernel wants are computed by the 16 diagonal threads in parallel at the end;
-//   * the column panel is exchanged as P[m][row] (8 x 128) and read with 128-bit loads: 32 instead of 128 shared loads
-//     per thread and step, ~4x fewer wavefronts (the row-major padded layout had 4-way conflicts on the column side).
-// Same outputs as factor_block up to rounding.  P: 8 * NB floats (16-byte aligned), D: 64 + 8 floats.
-__device__ __forceinline__ void factor_block_fast(float (&a)[8][8], float* P, float* D, float (*dall)[64], bool& bad,
-                                                  int ty, int tx) {
+constexpr int LS = NB + 1;  // row stride of L11 in shared memory: 8 rows apart = 8 banks apart (TRSM half of chol_panel_kernel)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Balanced factorisation for the panel kernel.  ncu on the register-tiled version (potf2-only launch, 35 us): 9 of 32
+// lanes active on average -- the trailing update keeps one 8 x 8 tile per thread, so the triangular shape and the
+// shrinking trailing matrix leave most lanes idle while every warp still issues the full 512-FMA tile update.
+// Here the block lives in shared memory as 4 x 4 micro-tiles in tile-major lower-triangular order (tile (ti, tk),
+// tk <= ti, at T + (ti (ti + 1) / 2 + tk) * 16: a thread moves its tile with four 128-bit accesses, consecutive
+// threads touch consecutive 64-byte chunks), and each of the 16 panel steps hands out exactly the work that exists:
+//   P1  thread 0 factors the 8 x 8 diagonal tile (3 micro-tiles) and publishes L_pp and the pivot reciprocals;
+//   P2  one thread per row below solves its 8 entries by substitution and writes them back and to the panel buffer
+//       Pn[m][row];
+//   P3  the g (g + 1) / 2 micro-tiles of the trailing lower triangle (g = (120 - 8 p) / 4) are dealt round-robin to the
+//       256 threads: 16 + 8 128-bit shared accesses for 128 FMAs.
+// ~4x fewer warp instructions than the register-tiled steps.  Outputs: Lsm (row-major, stride LS, upper part zero) and
+// dall (inverses of the 8 x 8 diagonal tiles).
+__device__ __forceinline__ float* mtile(float* T, int ti, int tk) { return T + (((ti * (ti + 1)) >> 1) + tk) * 16; }
+
+__device__ __forceinline__ void tri_index(int t, int& u, int& v) {  // t -> (u, v), v <= u, t = u (u + 1) / 2 + v
+  u = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (((u + 1) * (u + 2)) / 2 <= t) ++u;
+  while ((u * (u + 1)) / 2 > t) --u;
+  v = t - (u * (u + 1)) / 2;
+}
+
+__device__ __forceinline__ void factor_block_tiles(const float* Ajj, int64_t ld, int nb, float* T, float* Pn, float* D,
+                                                   float* Lsm, float (*dall)[64], bool& bad, int tid) {
+  constexpr int NT = NB / 4;                 // 32 micro-tile rows
+  constexpr int TILES = NT * (NT + 1) / 2;   // 528
+  // ---- load the lower triangle (identity padding for a short last block)
+  for (int q = tid; q < TILES; q += 256) {
+    int ti, tk;
+    tri_index(q, ti, tk);
+    float* dst = T + q * 16;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r = 4 * ti + a, c0 = 4 * tk;
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = (r == c0 + c) ? 1.0f : 0.0f;
+      if (r < nb) {
+        if (c0 + 3 < nb) {
+          const float4 g = *reinterpret_cast<const float4*>(Ajj + (int64_t)r * ld + c0);
+          v[0] = g.x; v[1] = g.y; v[2] = g.z; v[3] = g.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (c0 + c < nb) v[c] = Ajj[(int64_t)r * ld + c0 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c0 + c > r) v[c] = 0.0f;
+      }
+      *reinterpret_cast<float4*>(dst + 4 * a) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  __syncthreads();
 #pragma unroll 1
   for (int p = 0; p < 16; ++p) {
-    if (ty == p && tx == p) {
+    const int b = 8 * p + 8;     // first trailing row / column
+    const int R = NB - b;        // trailing size
+    if (tid == 0) {              // ---- P1: the 8 x 8 diagonal tile
+      float d[8][8];
+      float* t00 = mtile(T, 2 * p, 2 * p);
+      float* t10 = mtile(T, 2 * p + 1, 2 * p);
+      float* t11 = mtile(T, 2 * p + 1, 2 * p + 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          d[i][c] = t00[4 * i + c];
+          d[i][c + 4] = 0.0f;
+          d[i + 4][c] = t10[4 * i + c];
+          d[i + 4][c + 4] = t11[4 * i + c];
+        }
       float rl[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = a[j][j];
-        if (!(d > 0.0f)) bad = true;
-        float r = rsqrtf(d);
-        r = fmaf(r, fmaf(-0.5f * d * r, r, 0.5f), r);
-        rl[j] = r;
-        a[j][j] = d * r;
+      for (int jj = 0; jj < 8; ++jj) {
+        const float dv = d[jj][jj];
+        if (!(dv > 0.0f)) bad = true;
+        float r = rsqrtf(dv);
+        r = fmaf(r, fmaf(-0.5f * dv * r, r, 0.5f), r);
+        rl[jj] = r;
+        d[jj][jj] = dv * r;
 #pragma unroll
-        for (int i = j + 1; i < 8; ++i) a[i][j] *= r;
+        for (int i = jj + 1; i < 8; ++i) d[i][jj] *= r;
 #pragma unroll
-        for (int c = j + 1; c < 8; ++c)
+        for (int c = jj + 1; c < 8; ++c)
 #pragma unroll
-          for (int i = c; i < 8; ++i) a[i][c] = fmaf(-a[i][j], a[c][j], a[i][c]);
+          for (int i = c; i < 8; ++i) d[i][c] = fmaf(-d[i][jj], d[c][jj], d[i][c]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          if (c > i) a[i][c] = 0.0f;
-          D[i * 8 + c] = a[i][c];
+          if (c > i) d[i][c] = 0.0f;
+          D[i * 8 + c] = d[i][c];
         }
         D[64 + i] = rl[i];
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          t00[4 * i + c] = d[i][c];
+          t10[4 * i + c] = d[i + 4][c];
+          t11[4 * i + c] = d[i + 4][c + 4];
+        }
     }
     __syncthreads();
-    if (tx == p && ty >= p) {
-      if (ty > p) {  // L_ip = A_ip * L_pp^-T by substitution: x_c = (a_c - sum_{m < c} x_m l_cm) / l_cc, 8 rows in parallel
-        float l[8][8], r[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          r[c] = D[64 + c];
-#pragma unroll
-          for (int m = 0; m < 8; ++m) l[c][m] = D[c * 8 + m];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float acc = a[i][c];
-#pragma unroll
-            for (int m = 0; m < c; ++m) acc = fmaf(-a[i][m], l[c][m], acc);
-            a[i][c] = acc * r[c];
-          }
-        }
-      }
+    if (tid < R) {               // ---- P2: row i of the panel, x = a * L_pp^-T by substitution
+      const int i = b + tid;
+      const int ti = i >> 2, a = i & 3;
+      float* r0 = mtile(T, ti, 2 * p) + 4 * a;
+      float* r1 = mtile(T, ti, 2 * p + 1) + 4 * a;
+      const float4 x0 = *reinterpret_cast<const float4*>(r0), x1 = *reinterpret_cast<const float4*>(r1);
+      float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        *reinterpret_cast<float4*>(P + c * NB + ty * 8) = make_float4(a[0][c], a[1][c], a[2][c], a[3][c]);
-        *reinterpret_cast<float4*>(P + c * NB + ty * 8 + 4) = make_float4(a[4][c], a[5][c], a[6][c], a[7][c]);
+        float acc = x[c];
+#pragma unroll
+        for (int m = 0; m < c; ++m) acc = fmaf(-x[m], D[c * 8 + m], acc);
+        x[c] = acc * D[64 + c];
+      }
+      *reinterpret_cast<float4*>(r0) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(r1) = make_float4(x[4], x[5], x[6], x[7]);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) Pn[m * NB + i] = x[m];
+    }
+    __syncthreads();
+    {                            // ---- P3: trailing micro-tiles
+      const int g = R >> 2;
+      const int items = (g * (g + 1)) >> 1;
+      for (int t = tid; t < items; t += 256) {
+        int u, v;
+        tri_index(t, u, v);
+        const int ti = 2 * p + 2 + u, tk = 2 * p + 2 + v;
+        float* ct = mtile(T, ti, tk);
+        float4 c4[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) c4[a] = *reinterpret_cast<const float4*>(ct + 4 * a);
+        float acc[4][4] = {{c4[0].x, c4[0].y, c4[0].z, c4[0].w}, {c4[1].x, c4[1].y, c4[1].z, c4[1].w},
+                           {c4[2].x, c4[2].y, c4[2].z, c4[2].w}, {c4[3].x, c4[3].y, c4[3].z, c4[3].w}};
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float4 ra = *reinterpret_cast<const float4*>(Pn + m * NB + 4 * ti);
+          const float4 ca = *reinterpret_cast<const float4*>(Pn + m * NB + 4 * tk);
+          const float rr[4] = {ra.x, ra.y, ra.z, ra.w}, cc[4] = {ca.x, ca.y, ca.z, ca.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(-rr[a], cc[c], acc[a][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(ct + 4 * a) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
       }
     }
     __syncthreads();
-    if (ty > p && tx > p && tx <= ty) {  // trailing update of the lower tiles
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const float4 r0 = *reinterpret_cast<const float4*>(P + m * NB + ty * 8), r1 = *reinterpret_cast<const float4*>(P + m * NB + ty * 8 + 4);
-        const float4 c0 = *reinterpret_cast<const float4*>(P + m * NB + tx * 8), c1 = *reinterpret_cast<const float4*>(P + m * NB + tx * 8 + 4);
-        const float lr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-        const float lc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) a[i][c] = fmaf(-lr[i], lc[c], a[i][c]);
-      }
-    }
-    // P and D are rewritten only after the next iteration's first barrier
   }
-  if (ty == tx) {  // inverses of the 8 x 8 diagonal tiles, all 16 in parallel
-    float di[8][8];
+  if (tid < 16) {  // inverses of the 8 x 8 diagonal tiles, all 16 in parallel
+    float l[8][8], di[8][8];
+    const float* t00 = mtile(T, 2 * tid, 2 * tid);
+    const float* t10 = mtile(T, 2 * tid + 1, 2 * tid);
+    const float* t11 = mtile(T, 2 * tid + 1, 2 * tid + 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        l[i][c] = t00[4 * i + c];
+        l[i][c + 4] = 0.0f;
+        l[i + 4][c] = t10[4 * i + c];
+        l[i + 4][c + 4] = t11[4 * i + c];
+      }
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) di[i][jj] = 0.0f;
-      di[jj][jj] = __frcp_rn(a[jj][jj]);
+      di[jj][jj] = __frcp_rn(l[jj][jj]);
 #pragma unroll
       for (int i = jj + 1; i < 8; ++i) {
         float sacc = 0.f;
 #pragma unroll
-        for (int m = jj; m < i; ++m) sacc = fmaf(a[i][m], di[m][jj], sacc);
-        di[i][jj] = -sacc * __frcp_rn(a[i][i]);
+        for (int m = jj; m < i; ++m) sacc = fmaf(l[i][m], di[m][jj], sacc);
+        di[i][jj] = -sacc * __frcp_rn(l[i][i]);
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) dall[ty][i * 8 + c] = di[i][c];
+      for (int c = 0; c < 8; ++c) dall[tid][i * 8 + c] = di[i][c];
   }
+  // row-major copy for the TRSM half / the side buffer (upper part zero)
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 7, c = e & (NB - 1);
+    Lsm[r * LS + c] = (c <= r) ? mtile(T, r >> 2, c >> 2)[4 * (r & 3) + (c & 3)] : 0.0f;
+  }
+  __syncthreads();
 }
 
 // x = L^-1 for the factor held in `a` (dall from factor_block); x must enter as the identity tiles.
@@ -390,8 +484,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(float* A, int64_t ld, in
 // keeps L11 in shared memory and solves its own 128-row tile of the panel, L21 = A21 * L11^-T, with the same
 // 8-wide blocked steps (the 8 x 8 diagonal inverses come out of the factorisation).  The tile is written
 // back in place and as tf32 hi / lo planes (ld NB) for the SYRK GEMMs that follow.
-constexpr int LS = NB + 1;  // 8 rows apart = 8 banks apart (see the TRSM half of chol_panel_kernel)
-constexpr int PANEL_SMEM = (NB * LS + 2 * NB * PS + 16 * 64) * (int)sizeof(float);
+constexpr int PANEL_SMEM = (NB * LS + 2 * NB * PS + 16 * 64 + 528 * 16) * (int)sizeof(float);
 
 __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, int64_t j, int nb, int64_t m2,
                                                          float* Lblk, float* panelH, float* panelL, uint32_t* status) {
@@ -403,31 +496,15 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, i
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
   float* Ajj = A + j * ld + j;
-  float a[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int r = ty * 8 + i, cc = tx * 8 + c;
-      float v = (r == cc) ? 1.0f : 0.0f;
-      if (r < nb && cc < nb) v = (cc <= r) ? Ajj[(int64_t)r * ld + cc] : 0.0f;
-      a[i][c] = v;
-    }
+  float* Tt = reinterpret_cast<float*>(dall) + 16 * 64;   // [528][16] micro-tiles of the diagonal block
   bool bad = false;
-  factor_block_fast(a, P0, P1, dall, bad, ty, tx);  // P0: [8][NB] column panel, P1: diagonal tile + pivots
+  factor_block_tiles(Ajj, ld, nb, Tt, P0, P1, Lsm, dall, bad, tid);  // P0: [8][NB] panel, P1: diagonal tile + pivots
   if (blockIdx.x == 0) {
     // L11 goes to a side buffer [NB x NB]: the other CTAs of this launch are still reading Ajj
     if (bad && status) atomicOr(status, LCB_ST_NOT_SPD);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) Lblk[(ty * 8 + i) * NB + tx * 8 + c] = a[i][c];
+    for (int e = tid; e < NB * NB; e += 256) Lblk[e] = Lsm[(e >> 7) * LS + (e & (NB - 1))];
   }
   if (m2 <= 0) return;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) Lsm[(ty * 8 + i) * LS + tx * 8 + c] = a[i][c];
 
   // ---- my row tile of A21:  X = A21 L11^-T.  Rows are independent, so this half needs no block barrier: four
   // adjacent lanes share a pair of rows, lane `qd` owns the 8-column panels qd, qd + 4, qd + 8, qd + 12 of both rows
