@@ -494,7 +494,6 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(float* A, int64_t ld, i
   float* P1 = P0 + NB * PS;
   float(*dall)[64] = reinterpret_cast<float(*)[64]>(P1 + NB * PS);
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
   float* Ajj = A + j * ld + j;
   float* Tt = reinterpret_cast<float*>(dall) + 16 * 64;   // [528][16] micro-tiles of the diagonal block
   bool bad = false;
