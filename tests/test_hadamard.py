@@ -139,3 +139,21 @@ def test_fuse_layer_norms_and_rotate_model_match_reference_on_tiny_llama():
         if d:
             bad[k] = d
     assert not bad, bad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fwht_all_power_of_two_dims_like_the_reference_fwht_test(dtype):
+    """Mirror of the only asserting test in the reference tree (third_party/fast-hadamard-transform/tests/
+    test_fast_hadamard_transform.py:12-47: dims 1 .. 32768, batch 15): the transform against the exact fp64 result;
+    tolerance = the output dtype's rounding (fp32: 2e-6 relative to the row scale, bf16: one bf16 ulp)."""
+    from llm_compressor_b200 import hadamard as H
+    for logn in range(0, 16):
+        n = 1 << logn
+        g = torch.Generator().manual_seed(n)
+        x = torch.randn(15, n, generator=g).to(dtype)
+        exact = orc.matmul_hadU(x.double().numpy())
+        got = H.hadamard_rows(x.to(DEV), acc64=(n <= 16384)).double().cpu().numpy()
+        scale = np.abs(exact).max() + 1e-30
+        tol = 2e-6 if dtype == torch.float32 else 2.0 ** -8
+        assert np.max(np.abs(got - exact)) <= tol * scale, (n, float(np.max(np.abs(got - exact)) / scale))
