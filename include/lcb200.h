@@ -158,6 +158,10 @@ int lcb_rownorm_accum(float* s, const void* x, int64_t tokens, int64_t k, float 
  */
 int lcb_hessian_dead_fix(float* H, int64_t k, uint8_t* dead, void* stream);
 size_t lcb_chol_ws_bytes(int64_t k);
+/* development aid: with LCB_CHOL_TRACE=1 in the environment the tile-task kernel leaves 8 x uint64 per task
+ * (type|row|col, then globaltimer ns at fetch / accumulate-done / diagonal-flag / factor-done / end) at this byte
+ * offset of the workspace. */
+size_t lcb_chol_trace_offset(int64_t k);
 int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int64_t* perm, float damp, void* ws,
                        size_t ws_bytes, uint32_t* status, void* stream);
 
