@@ -689,8 +689,8 @@ __global__ void put_diag_blocks_kernel(float* A, int64_t k, const float* dinv_al
 //
 // The lower triangle of the work matrix is cut into 128 x 128 tiles.  A task owns one tile from start to finish
 // with the tile in registers (8 x 8 values per thread):
-//   L(i, c), i >= c:  acc = A(i,c) - sum_{j in [c0, c)} L(i,j) L(c,j)^T           (left-looking, exact fp32 FFMA)
-//                     i == c: potf2 of acc, Linv(c) = L(c,c)^-1 -> dinv[c]           (factor_tiles_core, invert_block)
+//   L(i, c), i >= c:  acc = A(i,c) - sum_{j in [c0, c)} L(i,j) L(c,j)^T           (left-looking, 3xTF32 tcgen05)
+//                     i == c: potf2 of acc fused with Linv(c) = L(c,c)^-1 -> dinv[c] (factor_invert_la, fp32 SIMT)
 //                     i >  c: L(i,c) = acc Linv(c)^T                                 (the panel TRSM as a GEMM)
 //   Y(k, c), k <  c:  acc = -sum_{j in [k, c)} Y(k,j) L(c,j)^T ;  Y(k,c) = acc Linv(c)^T     with Y = L^-T (the
 //                     transposed triangular inverse; Y(c,c) = Linv(c)^T is written by the diagonal task)
@@ -701,19 +701,16 @@ __global__ void put_diag_blocks_kernel(float* A, int64_t k, const float* dinv_al
 // its two tiles are flagged -- so only the last term, the TRSM and the potf2 of the diagonal tile are on the
 // critical path of the panel chain; everything else hides underneath it on the other SMs.
 // Operand tiles stream L2 -> shared memory with cp.async.cg in [128 rows][32 k] chunks, 16-byte pieces XOR-swizzled
-// by (row & 7): a thread owns rows ty + 16 a and columns tx + 16 b, so the eight lanes of a quarter warp read eight
-// different 16-byte columns (no bank conflicts) and a row / column pair needs one LDS.128 each per 4 k.
-constexpr int CT_STAGES = 3;
-constexpr int CT_CHUNK_FLOATS = NB * 32;                                  // 16 KB
-constexpr int CT_STAGE_FLOATS = 2 * CT_CHUNK_FLOATS;                      // P and Q chunk
-constexpr int CT_SMEM_FLOATS = CT_STAGES * CT_STAGE_FLOATS + NB * NB;     // stages + C tile (TRSM operand)
-constexpr int CT_SMEM = CT_SMEM_FLOATS * (int)sizeof(float);              // 160 KB
-static_assert(CT_SMEM >= PANEL_SMEM, "potf2 scratch must fit in the pipeline buffers");
-
+// by (row & 7) -- the K-major SWIZZLE_128B layout the tensor core reads (chol_tiles_tc_kernel below).
 struct TileArgs {
-  float* A;          // [k, k] work matrix, lower triangle (in: SPD block, out: L below the diagonal tiles)
-  float* Y;          // [k, k] transposed inverse (upper-triangular tiles), may be nullptr when with_inv == 0
-  float* dinv;       // [nblk][NB * NB] inverses of the diagonal tiles of L
+  // Every tile a task publishes is stored pre-split for the 3xTF32 products of its consumers: the tf32-rounded value
+  // in the matrix itself (hi), the exact remainder x - hi in the companion *lo matrix (hi + lo == x exactly).
+  float* A;          // [k, k] work matrix, lower triangle (in: SPD block, out: hi(L) below the diagonal tiles)
+  float* Alo;        // [k, k] lo(L)
+  float* Y;          // [k, k] hi of the transposed inverse Y = L^-T (upper-triangular tiles)
+  float* Ylo;        // [k, k] lo(Y)
+  float* dinv;       // [nblk][NB * NB] hi of the inverses of the diagonal tiles of L
+  float* dinv_lo;    // [nblk][NB * NB] lo
   uint32_t* flagL;   // [nblk * nblk]
   uint32_t* flagY;   // [nblk * nblk]
   uint32_t* counter;
@@ -747,277 +744,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// one [128 rows][32 floats] chunk of a row-major tile -> swizzled shared memory; rows >= rows_valid are zero-filled
-__device__ __forceinline__ void ct_load_chunk(float* dst, const float* tile, int64_t ld, int kofs, int rows_valid, int tid) {
-  const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int p = tid + 256 * u;
-    const int row = p >> 3, kq = p & 7;
-    const bool ok = row < rows_valid;
-    const float* src = tile + (int64_t)(ok ? row : 0) * ld + kofs + 4 * kq;
-    cp_async16(d0 + (uint32_t)(row * 128 + ((kq ^ (row & 7)) << 4)), src, ok ? 16 : 0);
-  }
-}
-
-// acc (-/+)= P Q^T over one 32-wide chunk.  MODE 0: all 8 x 8 blocks, acc -= ; MODE 1: blocks b <= a only (lower
-// triangle of a diagonal tile), acc -= ; MODE 2: blocks b >= bmin, acc +=  (Q lower triangular).
-template <int MODE>
-__device__ __forceinline__ void ct_chunk_fma(float (&acc)[8][8], const float* Ps, const float* Qs, int ty, int tx, int bmin) {
-  const float* pa = Ps + ty * 32;
-  const float* qb = Qs + tx * 32;
-  const int sa = ty & 7, sb = tx & 7;
-#pragma unroll 2
-  for (int kq = 0; kq < 8; ++kq) {
-    float4 av[8], bv[8];
-    const int oa = (kq ^ sa) << 2, ob = (kq ^ sb) << 2;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) av[a] = *reinterpret_cast<const float4*>(pa + a * 512 + oa);
-#pragma unroll
-    for (int b = 0; b < 8; ++b) bv[b] = *reinterpret_cast<const float4*>(qb + b * 512 + ob);
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        if (MODE == 1 && b > a) continue;
-        if (MODE == 2) {
-          if (b >= bmin) {
-            acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]);
-            acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
-            acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]);
-            acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
-          }
-        } else {
-          acc[a][b] = fmaf(-av[a].x, bv[b].x, acc[a][b]);
-          acc[a][b] = fmaf(-av[a].y, bv[b].y, acc[a][b]);
-          acc[a][b] = fmaf(-av[a].z, bv[b].z, acc[a][b]);
-          acc[a][b] = fmaf(-av[a].w, bv[b].w, acc[a][b]);
-        }
-      }
-  }
-}
-
-__global__ void __launch_bounds__(256, 1) chol_tiles_kernel(TileArgs g) {
-  extern __shared__ __align__(128) float csm[];
-  __shared__ int s_task[4];
-  float* stages = csm;
-  float* Cs = csm + CT_STAGES * CT_STAGE_FLOATS;
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  const int nblk = g.nblk;
-
-  for (;;) {
-    // ---------------- fetch the next task
-    if (tid == 0) {
-      const int t = (int)atomicAdd(g.counter, 1u);
-      int type = -1, ti = 0, tc = 0;
-      if (t < g.ntasks) {
-        int rem = t;
-        for (int c = g.c0; c < g.c1; ++c) {
-          const int nl = nblk - c;
-          const int ny = g.with_inv ? (c - g.c0) : 0;
-          if (rem < nl) { type = 0; ti = c + rem; tc = c; break; }
-          rem -= nl;
-          if (rem < ny) { type = 1; ti = g.c0 + rem; tc = c; break; }
-          rem -= ny;
-        }
-      }
-      s_task[0] = type; s_task[1] = ti; s_task[2] = tc; s_task[3] = t;
-    }
-    __syncthreads();
-    const int type = s_task[0], ti = s_task[1], c = s_task[2];
-    unsigned long long* tr = (g.trace != nullptr && tid == 0 && type >= 0) ? g.trace + (int64_t)s_task[3] * 8 : nullptr;
-    __syncthreads();
-    if (type < 0) break;
-    if (tr) { tr[0] = ((unsigned long long)type << 32) | ((unsigned long long)ti << 16) | (unsigned long long)c; tr[1] = gtime_ns(); }
-
-    // ---------------- operands of the accumulation  acc -= sum_j P_j Q_j^T
-    // L(i, c): P_j = L(i,j), Q_j = L(c,j), j in [c0, c)      Y(k, c): P_j = Y(k,j), Q_j = L(c,j), j in [k, c)
-    const bool isL = type == 0;
-    const bool diag = isL && ti == c;
-    const int j0 = isL ? g.c0 : ti;
-    const int nsteps = c - j0;
-    const float* Pbase = isL ? g.A + (int64_t)ti * NB * g.ld : g.Y + (int64_t)ti * NB * g.ld;
-    const uint32_t* Pflag = isL ? g.flagL + (int64_t)ti * nblk : g.flagY + (int64_t)ti * nblk;
-    const float* Qbase = g.A + (int64_t)c * NB * g.ld;
-    const uint32_t* Qflag = g.flagL + (int64_t)c * nblk;
-    const int prow_valid = min(NB, g.k - ti * NB);   // rows of the output tile
-    const int qrow_valid = min(NB, g.k - c * NB);    // columns of the output tile
-
-    float acc[8][8];
-    if (isL) {
-      const float* At = g.A + (int64_t)ti * NB * g.ld + (int64_t)c * NB;
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int r = ty + 16 * a, q = tx + 16 * b;
-          float v = 0.0f;
-          if (r < prow_valid && q < qrow_valid) v = __ldcg(At + (int64_t)r * g.ld + q);
-          else if (diag && r == q) v = 1.0f;   // identity padding of a short last block
-          acc[a][b] = v;
-        }
-    } else {
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
-    }
-
-    // ---------------- pipelined accumulation: chunk g = 4 * step + quarter
-    const int total = 4 * nsteps;
-    auto issue = [&](int gch) {
-      if (gch < total) {
-        const int step = gch >> 2, kofs = (j0 + step) * NB + (gch & 3) * 32;
-        float* st = stages + (gch % CT_STAGES) * CT_STAGE_FLOATS;
-        ct_load_chunk(st, Pbase, g.ld, kofs, prow_valid, tid);
-        if (!diag) ct_load_chunk(st + CT_CHUNK_FLOATS, Qbase, g.ld, kofs, qrow_valid, tid);
-      }
-      cp_async_commit();
-    };
-    auto poll = [&](int gch) {  // thread 0, before the barrier that precedes issue(gch)
-      if (gch < total && (gch & 3) == 0) {
-        const int j = j0 + (gch >> 2);
-        wait_flag(Pflag + j);
-        if (!diag) wait_flag(Qflag + j);
-      }
-    };
-    if (total > 0) {
-      if (tid == 0) poll(0);
-      __syncthreads();
-#pragma unroll
-      for (int gch = 0; gch < CT_STAGES - 1; ++gch) issue(gch);
-      for (int it = 0; it < total; ++it) {
-        const int gch = it + CT_STAGES - 1;
-        if (tid == 0) poll(gch);
-        __syncthreads();                    // chunk it-1 consumed by everyone; flags of gch known
-        issue(gch);
-        cp_async_wait<CT_STAGES - 1>();     // chunk `it` (own pieces) has landed
-        __syncthreads();
-        const float* st = stages + (it % CT_STAGES) * CT_STAGE_FLOATS;
-        if (diag) ct_chunk_fma<1>(acc, st, st, ty, tx, 0);
-        else ct_chunk_fma<0>(acc, st, st + CT_CHUNK_FLOATS, ty, tx, 0);
-      }
-      cp_async_wait<0>();
-      __syncthreads();
-    }
-    if (tr) tr[2] = gtime_ns();
-
-    if (diag) {
-      // ---------------- potf2 of the diagonal tile + inverse of the factor
-      float* Lsm = csm;                       // [NB][LS]
-      float* P0 = Lsm + NB * LS;
-      float* P1 = P0 + NB * PS;
-      float(*dall)[64] = reinterpret_cast<float(*)[64]>(P1 + NB * PS);
-      float* Tt = reinterpret_cast<float*>(dall) + 16 * 64;
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (b > a) continue;
-          const int r = ty + 16 * a, q = tx + 16 * b;
-          if ((q >> 2) <= (r >> 2)) mtile(Tt, r >> 2, q >> 2)[4 * (r & 3) + (q & 3)] = (q <= r) ? acc[a][b] : 0.0f;
-        }
-      __syncthreads();
-      bool bad = false;
-      factor_tiles_core(Tt, P0, P1, Lsm, dall, bad, tid);
-      if (bad && g.status) atomicOr(g.status, LCB_ST_NOT_SPD);
-      if (tr) tr[4] = gtime_ns();
-      {
-        float a8[8][8], x8[8][8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = ty * 8 + i, cc = tx * 8 + q;
-            a8[i][q] = Lsm[r * LS + cc];
-            x8[i][q] = (r == cc) ? 1.0f : 0.0f;
-          }
-        __syncthreads();  // Lsm read by everyone before P0 / P1 are reused
-        invert_block(a8, x8, P0, P1, dall, ty, tx);
-        float* dv = g.dinv + (int64_t)c * NB * NB;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = ty * 8 + i;
-          float4 v0, v1;
-          v0.x = (tx * 8 + 0 <= r) ? x8[i][0] : 0.0f; v0.y = (tx * 8 + 1 <= r) ? x8[i][1] : 0.0f;
-          v0.z = (tx * 8 + 2 <= r) ? x8[i][2] : 0.0f; v0.w = (tx * 8 + 3 <= r) ? x8[i][3] : 0.0f;
-          v1.x = (tx * 8 + 4 <= r) ? x8[i][4] : 0.0f; v1.y = (tx * 8 + 5 <= r) ? x8[i][5] : 0.0f;
-          v1.z = (tx * 8 + 6 <= r) ? x8[i][6] : 0.0f; v1.w = (tx * 8 + 7 <= r) ? x8[i][7] : 0.0f;
-          *reinterpret_cast<float4*>(dv + r * NB + tx * 8) = v0;
-          *reinterpret_cast<float4*>(dv + r * NB + tx * 8 + 4) = v1;
-        }
-        __syncthreads();
-        if (tid == 0) { __threadfence(); st_release_u32(g.flagL + (int64_t)c * nblk + c, 1u); }
-        if (tr) tr[5] = gtime_ns();
-        if (g.with_inv) {  // Y(c, c) = Linv(c)^T
-          float* Yt = g.Y + (int64_t)c * NB * g.ld + (int64_t)c * NB;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int r = ty * 8 + i, cc = tx * 8 + q;   // Linv[r][cc] -> Y[cc][r]
-              if (r < qrow_valid && cc < qrow_valid) Yt[(int64_t)cc * g.ld + r] = (cc <= r) ? x8[i][q] : 0.0f;
-            }
-          __syncthreads();
-          if (tid == 0) { __threadfence(); st_release_u32(g.flagY + (int64_t)c * nblk + c, 1u); }
-        }
-      }
-      __syncthreads();
-      continue;
-    }
-
-    // ---------------- out = acc Linv(c)^T   (A operand from shared memory, Linv streamed through the stage buffers)
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const int r = ty + 16 * a, m = tx + 16 * b;
-        const int mm = m & 31;
-        Cs[(m >> 5) * CT_CHUNK_FLOATS + r * 32 + ((((mm >> 2) ^ (r & 7)) << 2) | (mm & 3))] = acc[a][b];
-      }
-    if (tid == 0) wait_flag(g.flagL + (int64_t)c * nblk + c);
-    if (tr) tr[3] = gtime_ns();
-    __syncthreads();
-    {
-      const float* dv = g.dinv + (int64_t)c * NB * NB;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) ct_load_chunk(stages + ch * CT_CHUNK_FLOATS, dv, NB, ch * 32, NB, tid);
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncthreads();
-    }
-    float out[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 8; ++b) out[a][b] = 0.0f;
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch)
-      ct_chunk_fma<2>(out, Cs + ch * CT_CHUNK_FLOATS, stages + ch * CT_CHUNK_FLOATS, ty, tx, 2 * ch);
-    {
-      float* Ot = (isL ? g.A : g.Y) + (int64_t)ti * NB * g.ld + (int64_t)c * NB;
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const int r = ty + 16 * a;
-        if (r < prow_valid) {
-#pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const int q = tx + 16 * b;
-            if (q < qrow_valid) Ot[(int64_t)r * g.ld + q] = out[a][b];
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      st_release_u32((isL ? g.flagL : g.flagY) + (int64_t)ti * nblk + c, 1u);
-    }
-    if (tr) tr[5] = gtime_ns();
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Fused potf2 + inverse of a 128 x 128 diagonal tile with look-ahead (the serial heart of the panel chain).
 // In: T = lower triangle in micro-tile layout (see factor_block_tiles).  Out: W = L^-1 in the same layout.
@@ -1029,7 +755,14 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_kernel(TileArgs g) {
 // trailing micro-tiles of T and of W (forward substitution on the identity: W(i,:) -= L(i,p) W_p), the tiles the
 // chain warp needs next first.  Hand-offs are named barriers (arrive on the producer side, sync on the consumer
 // side); panel buffers are double-buffered by step parity.
-constexpr int FI_T_FLOATS = 528 * 16;
+// Micro-tile storage of factor_invert_la: row a (0..3) of micro-tile t = ti (ti + 1) / 2 + tk lives in plane a at
+// float4 index t, so the lanes of a warp that work on consecutive micro-tiles touch consecutive 16-byte words (the
+// tile-major layout of factor_block_tiles puts them 64 bytes apart: 4-way bank conflicts, and the trailing update is
+// bound by shared-memory wavefronts, not by FMAs).  Planes are 32 bytes out of phase so that the four rows of one
+// micro-tile sit in different banks as well.
+constexpr int FI_NT = 528;
+constexpr int FI_PLANE = FI_NT * 4 + 8;          // floats per plane
+constexpr int FI_T_FLOATS = 4 * FI_PLANE;
 constexpr int FI_SMEM_FLOATS = 2 * FI_T_FLOATS + 2 * 8 * NB + 2 * 8 * NB + 2 * 64;
 enum { FI_BAR_P1 = 1, FI_BAR_LA = 2, FI_BAR_P3A = 3, FI_BAR_W = 4, FI_BAR_P1B = 5 };  // P1 alternates ids by step parity:
 // the chain warp may arrive for step p+1 before every worker has arrived for step p
@@ -1038,12 +771,15 @@ __device__ __forceinline__ void nbar_arrive(int id, int n) {
   __threadfence_block();
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+__device__ __forceinline__ int fi_tidx(int ti, int tk) { return ((ti * (ti + 1)) >> 1) + tk; }
+__device__ __forceinline__ float* fi_row(float* T, int ti, int tk, int a) { return T + a * FI_PLANE + (fi_tidx(ti, tk) << 2); }
 
-// C(ti,tk) -= sum_m rowp[m][4 ti ..] * colp[m][4 tk ..]
-__device__ __forceinline__ void fi_tile_update(float* ct, const float* rowp, const float* colp, int ti, int tk) {
+// C(t) -= sum_m rowp[m][4 ti ..] * colp[m][4 tk ..]
+__device__ __forceinline__ void fi_tile_update(float* M, int t, const float* rowp, const float* colp, int ti, int tk) {
+  float* ct = M + (t << 2);
   float4 c4[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) c4[a] = *reinterpret_cast<const float4*>(ct + 4 * a);
+  for (int a = 0; a < 4; ++a) c4[a] = *reinterpret_cast<const float4*>(ct + a * FI_PLANE);
   float acc[4][4] = {{c4[0].x, c4[0].y, c4[0].z, c4[0].w}, {c4[1].x, c4[1].y, c4[1].z, c4[1].w},
                      {c4[2].x, c4[2].y, c4[2].z, c4[2].w}, {c4[3].x, c4[3].y, c4[3].z, c4[3].w}};
 #pragma unroll
@@ -1057,20 +793,22 @@ __device__ __forceinline__ void fi_tile_update(float* ct, const float* rowp, con
       for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(-rr[a], cc[c], acc[a][c]);
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(ct + 4 * a) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+  for (int a = 0; a < 4; ++a)
+    *reinterpret_cast<float4*>(ct + a * FI_PLANE) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
 }
 
-__device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, float* Wp, float* D, bool& bad, int tid) {
+__device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, float* Wp, float* D, bool& bad, int tid,
+                                                 long long* dbg = nullptr) {
+#define FI_DBG(slot) do { if (dbg) dbg[p * 12 + (slot)] = clock64(); } while (0)
   // W = identity
-  for (int q = tid; q < 528; q += 256) {
+  for (int q = tid; q < FI_NT; q += 256) {
     int ti, tk;
     tri_index(q, ti, tk);
-    float* dst = W + q * 16;
     const float dg = (ti == tk) ? 1.0f : 0.0f;
-    *reinterpret_cast<float4*>(dst + 0) = make_float4(dg, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(0.f, dg, 0.f, 0.f);
-    *reinterpret_cast<float4*>(dst + 8) = make_float4(0.f, 0.f, dg, 0.f);
-    *reinterpret_cast<float4*>(dst + 12) = make_float4(0.f, 0.f, 0.f, dg);
+    *reinterpret_cast<float4*>(W + 0 * FI_PLANE + 4 * q) = make_float4(dg, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(W + 1 * FI_PLANE + 4 * q) = make_float4(0.f, dg, 0.f, 0.f);
+    *reinterpret_cast<float4*>(W + 2 * FI_PLANE + 4 * q) = make_float4(0.f, 0.f, dg, 0.f);
+    *reinterpret_cast<float4*>(W + 3 * FI_PLANE + 4 * q) = make_float4(0.f, 0.f, 0.f, dg);
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -1080,16 +818,14 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
     for (int p = 0; p < 16; ++p) {
       float* Dv = D + (p & 1) * 64;      // Dinv of this step, row-major 8 x 8
       float* Pp = Pn + (p & 1) * 8 * NB;
+      if (lane == 0) FI_DBG(0);
       if (lane == 0) {
         float d[8][8];
-        const float* t00 = mtile(T, 2 * p, 2 * p);
-        const float* t10 = mtile(T, 2 * p + 1, 2 * p);
-        const float* t11 = mtile(T, 2 * p + 1, 2 * p + 1);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 a = *reinterpret_cast<const float4*>(t00 + 4 * i);
-          const float4 b = *reinterpret_cast<const float4*>(t10 + 4 * i);
-          const float4 c = *reinterpret_cast<const float4*>(t11 + 4 * i);
+          const float4 a = *reinterpret_cast<const float4*>(fi_row(T, 2 * p, 2 * p, i));
+          const float4 b = *reinterpret_cast<const float4*>(fi_row(T, 2 * p + 1, 2 * p, i));
+          const float4 c = *reinterpret_cast<const float4*>(fi_row(T, 2 * p + 1, 2 * p + 1, i));
           d[i][0] = a.x; d[i][1] = a.y; d[i][2] = a.z; d[i][3] = a.w;
           d[i][4] = 0.f; d[i][5] = 0.f; d[i][6] = 0.f; d[i][7] = 0.f;
           d[i + 4][0] = b.x; d[i + 4][1] = b.y; d[i + 4][2] = b.z; d[i + 4][3] = b.w;
@@ -1133,21 +869,23 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
       }
       __syncwarp();
       nbar_arrive((p & 1) ? FI_BAR_P1B : FI_BAR_P1, 256);
+      if (lane == 0) FI_DBG(1);
       if (p < 15) {
         if (p >= 1) nbar_sync(FI_BAR_P3A, 256);   // T(p+1,p) and T(p+1,p+1) carry the updates of steps < p
         // ---- look-ahead: the 8 rows below the diagonal tile, then the next diagonal tile
         const int r = lane >> 2, cg = lane & 3;          // row r of the 8, columns 2 cg and 2 cg + 1
         const int gi = 8 * (p + 1) + r;
-        const float* trow0 = mtile(T, gi >> 2, 2 * p) + 4 * (gi & 3);
-        const float* trow1 = mtile(T, gi >> 2, 2 * p + 1) + 4 * (gi & 3);
-        const float4 x0 = *reinterpret_cast<const float4*>(trow0), x1 = *reinterpret_cast<const float4*>(trow1);
+        const float4 x0 = *reinterpret_cast<const float4*>(fi_row(T, gi >> 2, 2 * p, gi & 3));
+        const float4 x1 = *reinterpret_cast<const float4*>(fi_row(T, gi >> 2, 2 * p + 1, gi & 3));
+        if (lane == 0) FI_DBG(2);
         const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = 2 * cg + q;
-          float acc = 0.f;
-#pragma unroll
-          for (int m = 0; m < 8; ++m) acc = fmaf(xr[m], Dv[c * 8 + m], acc);   // Dinv[c][m] == 0 for m > c
+          const float4 d0 = *reinterpret_cast<const float4*>(Dv + 8 * c), d1 = *reinterpret_cast<const float4*>(Dv + 8 * c + 4);
+          float acc = xr[0] * d0.x;                       // Dinv[c][m] == 0 for m > c
+          acc = fmaf(xr[1], d0.y, acc); acc = fmaf(xr[2], d0.z, acc); acc = fmaf(xr[3], d0.w, acc);
+          acc = fmaf(xr[4], d1.x, acc); acc = fmaf(xr[5], d1.y, acc); acc = fmaf(xr[6], d1.z, acc); acc = fmaf(xr[7], d1.w, acc);
           Pp[c * NB + gi] = acc;
         }
         __syncwarp();
@@ -1163,13 +901,14 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
               float acc = 0.f;
 #pragma unroll
               for (int m = 0; m < 8; ++m) acc = fmaf(li[m], Pp[m * NB + gc], acc);
-              float* e = mtile(T, gi >> 2, gc >> 2) + 4 * (gi & 3) + (gc & 3);
+              float* e = fi_row(T, gi >> 2, gc >> 2, gi & 3) + (gc & 3);
               *e -= acc;
             }
           }
         }
         __syncwarp();
         nbar_arrive(FI_BAR_LA, 256);
+        if (lane == 0) FI_DBG(3);
       }
     }
   } else {
@@ -1181,18 +920,25 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
       float* Pp = Pn + (p & 1) * 8 * NB;
       float* Wq = Wp + (p & 1) * 8 * NB;
       nbar_sync((p & 1) ? FI_BAR_P1B : FI_BAR_P1, 256);
+      float dv[8][8];   // Dinv (lower triangle), broadcast loads
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 d0 = *reinterpret_cast<const float4*>(Dv + 8 * c), d1 = *reinterpret_cast<const float4*>(Dv + 8 * c + 4);
+        dv[c][0] = d0.x; dv[c][1] = d0.y; dv[c][2] = d0.z; dv[c][3] = d0.w;
+        dv[c][4] = d1.x; dv[c][5] = d1.y; dv[c][6] = d1.z; dv[c][7] = d1.w;
+      }
+      if (wt == 0) FI_DBG(4);
       {  // ---- panel solve for row i (the chain warp does rows 8(p+1) .. 8(p+1)+7)
         const int i = 8 * (p + 2) + wt;
         if (i < NB) {
-          const float* t0 = mtile(T, i >> 2, 2 * p) + 4 * (i & 3);
-          const float* t1 = mtile(T, i >> 2, 2 * p + 1) + 4 * (i & 3);
-          const float4 x0 = *reinterpret_cast<const float4*>(t0), x1 = *reinterpret_cast<const float4*>(t1);
+          const float4 x0 = *reinterpret_cast<const float4*>(fi_row(T, i >> 2, 2 * p, i & 3));
+          const float4 x1 = *reinterpret_cast<const float4*>(fi_row(T, i >> 2, 2 * p + 1, i & 3));
           const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float acc = 0.f;
 #pragma unroll
-            for (int m = 0; m <= c; ++m) acc = fmaf(xr[m], Dv[c * 8 + m], acc);
+            for (int m = 0; m <= c; ++m) acc = fmaf(xr[m], dv[c][m], acc);
             Pp[c * NB + i] = acc;
           }
         }
@@ -1205,19 +951,20 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
             const int rr = 8 * p + m;
-            w[m] = (tk <= (rr >> 2)) ? mtile(W, rr >> 2, tk)[4 * (rr & 3) + cc] : 0.0f;
+            w[m] = (tk <= (rr >> 2)) ? fi_row(W, rr >> 2, tk, rr & 3)[cc] : 0.0f;
           }
 #pragma unroll
-          for (int m = 7; m >= 0; --m) {
+          for (int m = 0; m < 8; ++m) {
             float acc = 0.f;
 #pragma unroll
-            for (int q = 0; q <= m; ++q) acc = fmaf(Dv[m * 8 + q], w[q], acc);
+            for (int q = 0; q <= m; ++q) acc = fmaf(dv[m][q], w[q], acc);
             const int rr = 8 * p + m;
-            if (tk <= (rr >> 2)) mtile(W, rr >> 2, tk)[4 * (rr & 3) + cc] = acc;
+            if (tk <= (rr >> 2)) fi_row(W, rr >> 2, tk, rr & 3)[cc] = acc;
             Wq[m * NB + col] = acc;
           }
         }
       }
+      if (wt == 0) FI_DBG(5);
       if (p < 15) nbar_sync(FI_BAR_LA, 256);   // every panel entry of this step (workers' and the chain warp's) is written
       else nbar_sync(FI_BAR_W, 224);
       if (p < 15) {
@@ -1234,23 +981,26 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
             if (it < nA - 3) {
               int u, v;
               tri_index(it + 3, u, v);
-              fi_tile_update(mtile(T, base + u, base + v), Pp, Pp, base + u, base + v);
+              fi_tile_update(T, fi_tidx(base + u, base + v), Pp, Pp, base + u, base + v);
             } else {
               const int w2 = it - (nA - 3);
               const int u = w2 / nWc, v = w2 - u * nWc;
-              fi_tile_update(mtile(W, base + u, v), Pp, Wq, base + u, v);
+              fi_tile_update(W, fi_tidx(base + u, v), Pp, Wq, base + u, v);
             }
           }
           if (first) {
             first = false;
             if (p < 14) nbar_arrive(FI_BAR_P3A, 256);   // items 3..9 (the chain warp's next inputs) are in the first round
+            if (wt == 0) FI_DBG(7);
           }
         }
       }
+      if (wt == 0) FI_DBG(8);
       nbar_sync(FI_BAR_W, 224);
     }
   }
   __syncthreads();
+#undef FI_DBG
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1265,13 +1015,28 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
 constexpr int TT_STAGES = 3;
 constexpr int TT_PLANE = NB * 32 * 4;                // 16 KB: one [128][32] fp32 chunk
 constexpr int TT_STAGE_BYTES = 4 * TT_PLANE;         // P hi, Q hi, P lo, Q lo
-constexpr int TT_SMEM = TT_STAGES * TT_STAGE_BYTES + 1024 + 256;   // + alignment slack + barriers
+constexpr int TT_XPLANES = 10 * 4096;                // Linv chunk ch keeps rows >= 32 ch only: 16 + 12 + 8 + 4 KB
+constexpr int TT_DATA_BYTES = 8 * TT_PLANE + 2 * TT_XPLANES;       // TRSM phase: C hi / lo (128 KB) + Linv hi / lo (80 KB)
+constexpr int TT_SMEM = TT_DATA_BYTES + 1024 + 256;  // + alignment slack + barriers
+static_assert(TT_DATA_BYTES >= TT_STAGES * TT_STAGE_BYTES, "pipeline stages must fit");
+static_assert(TT_DATA_BYTES >= 2 * NB * 132 * 4, "output staging must fit");
+enum { TT_BAR_WORK = 6, TT_BAR_FULL0 = 7 };          // named barriers 7, 8, 9: stage s handed to the MMA warp
 constexpr int TT_DRAIN = 8;                          // chunks per TMEM accumulation chain (256 columns)
 static_assert(TT_STAGES * TT_STAGE_BYTES >= FI_SMEM_FLOATS * 4, "potf2 scratch must fit in the pipeline buffers");
 
 __device__ __forceinline__ void umma_tf32_128(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
   // c_format F32, a/b TF32, K-major both, N = 128, M = 128
   constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_n(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t n, uint32_t accumulate) {
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -1289,20 +1054,13 @@ __device__ __forceinline__ uint64_t tt_desc(uint32_t saddr) {  // K-major, SWIZZ
   d |= (uint64_t)2 << 61;
   return d;
 }
-// in place: x -> hi = tf32(x) (round to nearest), lo plane = x - hi; `planes` consecutive 16 KB planes at `hi`
-__device__ __forceinline__ void tt_split(uint8_t* hi, uint8_t* lo, int planes, int tid) {
-  const int pieces = planes * (TT_PLANE / 16);
-  for (int p = tid; p < pieces; p += 256) {
-    float4 v = *reinterpret_cast<const float4*>(hi + p * 16);
-    float4 h, l;
-    uint32_t b;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.x)); h.x = __uint_as_float(b); l.x = __fsub_rn(v.x, h.x);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y)); h.y = __uint_as_float(b); l.y = __fsub_rn(v.y, h.y);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.z)); h.z = __uint_as_float(b); l.z = __fsub_rn(v.z, h.z);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.w)); h.w = __uint_as_float(b); l.w = __fsub_rn(v.w, h.w);
-    *reinterpret_cast<float4*>(hi + p * 16) = h;
-    *reinterpret_cast<float4*>(lo + p * 16) = l;
-  }
+// x = hi + lo exactly, hi = tf32(x) (round to nearest)
+__device__ __forceinline__ void tt_split4(const float4 v, float4& h, float4& l) {
+  uint32_t b;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.x)); h.x = __uint_as_float(b); l.x = __fsub_rn(v.x, h.x);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y)); h.y = __uint_as_float(b); l.y = __fsub_rn(v.y, h.y);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.z)); h.z = __uint_as_float(b); l.z = __fsub_rn(v.z, h.z);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.w)); h.w = __uint_as_float(b); l.w = __fsub_rn(v.w, h.w);
 }
 // the 12 MMAs of one 32-wide chunk: D (+)= (Ah + Al)(Bh + Bl)^T without the lo * lo term, small terms first
 __device__ __forceinline__ void tt_mma_chunk(uint32_t tmem_d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, bool first) {
@@ -1315,18 +1073,30 @@ __device__ __forceinline__ void tt_mma_chunk(uint32_t tmem_d, uint32_t ah, uint3
     umma_tf32_128(tmem_d, dah, dbh, 1u);
   }
 }
-__device__ __forceinline__ void tt_load_plane(uint8_t* dst, const float* tile, int64_t ld, int kofs, int rows_valid, int tid) {
-  ct_load_chunk(reinterpret_cast<float*>(dst), tile, ld, kofs, rows_valid, tid);
+// rows [row0, 128) of one [128][32]-float chunk of a row-major tile -> dst (row - row0 at 128 bytes each, 16-byte pieces
+// XOR-swizzled by row & 7; row0 % 8 == 0); rows >= rows_valid are zero-filled.  NT = number of loading threads.
+template <int NT>
+__device__ __forceinline__ void tt_load_plane(uint8_t* dst, const float* tile, int64_t ld, int kofs, int rows_valid, int tid,
+                                              int row0 = 0) {
+  const uint32_t d0 = smem_u32(dst);
+  const int pieces = (NB - row0) * 8;
+  for (int p = tid; p < pieces; p += NT) {
+    const int rl = p >> 3, kq = p & 7, row = row0 + rl;
+    const bool ok = row < rows_valid;
+    const float* src = tile + (int64_t)(ok ? row : 0) * ld + kofs + 4 * kq;
+    cp_async16(d0 + (uint32_t)(rl * 128 + ((kq ^ (row & 7)) << 4)), src, ok ? 16 : 0);
+  }
 }
 
 __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
   extern __shared__ uint8_t tsm_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsm_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TT_STAGES * TT_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TT_DATA_BYTES);
   uint64_t* mma_done = bars;          // [TT_STAGES]
   uint64_t* acc_done = bars + TT_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TT_STAGES + 1);
   __shared__ int s_task[4];
+  __shared__ int s_cnt[2];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int R = 32 * (warp & 3) + lane;       // my row of the tile
@@ -1379,9 +1149,11 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
     const bool diag = isL && ti == c;
     const int j0 = isL ? g.c0 : ti;
     const int nsteps = c - j0;
-    const float* Pbase = isL ? g.A + (int64_t)ti * NB * g.ld : g.Y + (int64_t)ti * NB * g.ld;
+    const float* Pbase = (isL ? g.A : g.Y) + (int64_t)ti * NB * g.ld;
+    const float* Pbase_lo = (isL ? g.Alo : g.Ylo) + (int64_t)ti * NB * g.ld;
     const uint32_t* Pflag = isL ? g.flagL + (int64_t)ti * nblk : g.flagY + (int64_t)ti * nblk;
     const float* Qbase = g.A + (int64_t)c * NB * g.ld;
+    const float* Qbase_lo = g.Alo + (int64_t)c * NB * g.ld;
     const uint32_t* Qflag = g.flagL + (int64_t)c * nblk;
     const int prow_valid = min(NB, g.k - ti * NB);
     const int qrow_valid = min(NB, g.k - c * NB);
@@ -1413,21 +1185,27 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
     }
 
     // ---------------- pipelined accumulation  C -= sum_j P_j Q_j^T   (chunk = 4 * step + quarter)
+    // Warps 0..6 are LOADERS (cp.async of the four planes of a chunk, up to two chunks ahead), warp 7 is the MMA warp: it
+    // takes a stage over through a named barrier, issues the 12 MMAs (the issue blocks for about their execution time)
+    // and commits to the stage's mbarrier, which the loaders wait on before they overwrite that stage.
     const int total = 4 * nsteps;
     auto issue = [&](int gch) {
-      if (gch < total) {
-        const int step = gch >> 2, kofs = (j0 + step) * NB + (gch & 3) * 32;
-        uint8_t* st = sm + (gch % TT_STAGES) * TT_STAGE_BYTES;
-        tt_load_plane(st, Pbase, g.ld, kofs, prow_valid, tid);
-        if (!diag) tt_load_plane(st + TT_PLANE, Qbase, g.ld, kofs, qrow_valid, tid);
+      const int step = gch >> 2, kofs = (j0 + step) * NB + (gch & 3) * 32;
+      uint8_t* st = sm + (gch % TT_STAGES) * TT_STAGE_BYTES;
+      tt_load_plane<224>(st, Pbase, g.ld, kofs, prow_valid, tid);
+      tt_load_plane<224>(st + 2 * TT_PLANE, Pbase_lo, g.ld, kofs, prow_valid, tid);
+      if (!diag) {
+        tt_load_plane<224>(st + TT_PLANE, Qbase, g.ld, kofs, qrow_valid, tid);
+        tt_load_plane<224>(st + 3 * TT_PLANE, Qbase_lo, g.ld, kofs, qrow_valid, tid);
       }
-      cp_async_commit();   // one group per chunk (empty past the end)
+      cp_async_commit();   // one group per chunk
     };
     auto flags_ready = [&](int gch) -> bool {  // thread 0: may chunk gch be loaded (non-blocking)?
       if ((gch & 3) != 0) return true;
       const int j = j0 + (gch >> 2);
-      if (ld_acquire_u32(Pflag + j) == 0u) return false;
-      return diag || ld_acquire_u32(Qflag + j) != 0u;
+      const uint32_t fp = ld_acquire_u32(Pflag + j);                 // both loads in flight together
+      const uint32_t fq = diag ? 1u : ld_acquire_u32(Qflag + j);
+      return fp != 0u && fq != 0u;
     };
     auto poll_block = [&](int gch) {            // thread 0: wait until chunk gch may be loaded
       if ((gch & 3) == 0) {
@@ -1448,69 +1226,77 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) creg[32 + j] -= v[j];
       asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncthreads();   // all eight warps: nobody starts the next accumulation chain while TMEM is still being read
     };
     if (total > 0) {
-      // Loads run up to two chunks ahead of the MMAs.  A step's tiles may not be flagged yet: thread 0 then checks
-      // WITHOUT blocking while there is still work in the pipeline (the chunks already loaded keep flowing into the
-      // tensor core) and blocks only when the pipeline has run dry.
-      if (tid == 0) poll_block(0);
-      __syncthreads();
-      issue(0);
-      issue(1);
-      int issued = 2;
-      int chain = 0;  // chunks in the current TMEM accumulation chain
-      for (int it = 0; it < total; ++it) {
-        const int s = it % TT_STAGES;
-        uint8_t* st = sm + s * TT_STAGE_BYTES;
-        if (issued <= it) {                               // pipeline dry: chunk `it` opens a step whose tiles were not ready
-          if (tid == 0) poll_block(it);
-          __syncthreads();
-          issue(it);
-          issued = it + 1;
-        }
-        const int pend = issued - it - 1;                 // younger groups that may stay in flight
-        if (pend >= 2) cp_async_wait<2>();
-        else if (pend == 1) cp_async_wait<1>();
-        else cp_async_wait<0>();
-        __syncthreads();                                  // every piece of chunk `it` has landed
-        if (diag) tt_split(st, st + 2 * TT_PLANE, 1, tid);
-        else tt_split(st, st + 2 * TT_PLANE, 2, tid);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (tid == 0) {                                   // how many of the chunks up to it+2 can be loaded now?
-          int cnt = 0;
-          for (int gch = issued; gch <= it + 2 && gch < total; ++gch) {
-            if (!flags_ready(gch)) break;
-            ++cnt;
+      if (warp < 7) {
+        // ---- loaders.  A step's tiles may not be flagged yet: thread 0 checks WITHOUT blocking while chunks are still
+        // in flight and blocks only when the pipeline has run dry.
+        if (tid == 0) poll_block(0);
+        nbar_sync(TT_BAR_WORK, 224);
+        issue(0);
+        issue(1);
+        int issued = 2;
+        int chain = 0;
+        for (int it = 0; it < total; ++it) {
+          const int s = it % TT_STAGES;
+          if (issued <= it) {                               // pipeline dry: chunk `it` opens a step whose tiles were not ready
+            if (tid == 0) poll_block(it);
+            nbar_sync(TT_BAR_WORK, 224);
+            issue(it);
+            issued = it + 1;
           }
-          s_task[3] = cnt;
+          const int pend = issued - it - 1;                 // younger groups that may stay in flight
+          if (pend >= 2) cp_async_wait<2>();
+          else if (pend == 1) cp_async_wait<1>();
+          else cp_async_wait<0>();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my landed pieces -> visible to the tensor core
+          nbar_arrive(TT_BAR_FULL0 + s, 256);
+          if (tid == 0) {                                   // how many of the chunks up to it+2 can be loaded now?
+            int cnt = 0;
+            for (int gch = issued; gch <= it + 2 && gch < total; ++gch) {
+              if (!flags_ready(gch)) break;
+              ++cnt;
+            }
+            s_cnt[it & 1] = cnt;
+          }
+          nbar_sync(TT_BAR_WORK, 224);
+          const int can_issue = s_cnt[it & 1];
+          const bool do_drain = it == total - 1 || chain + 1 == TT_DRAIN;
+          if (it >= 1) {                                    // the stage of chunk it+2 is the stage of chunk it-1
+            const int sp = (it - 1) % TT_STAGES;
+            mbar_wait(&mma_done[sp], (par_done >> sp) & 1u);
+            par_done ^= 1u << sp;
+          }
+          for (int q = 0; q < can_issue; ++q) issue(issued++);
+          if (do_drain) { drain(); chain = 0; } else { ++chain; }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();                                  // planes visible to the tensor core; s_task[3] valid
-        const int can_issue = s_task[3];
-        const bool last = it == total - 1;
-        const bool do_drain = last || chain + 1 == TT_DRAIN;
-        if (tid == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;");
-          const uint32_t ph = smem_u32(st), pl = ph + 2 * TT_PLANE;
-          const uint32_t qh = diag ? ph : ph + TT_PLANE, ql = diag ? pl : pl + TT_PLANE;
-          tt_mma_chunk(tmem_base, ph, pl, qh, ql, chain == 0);
-          umma_commit(&mma_done[s]);
-          if (do_drain) umma_commit(acc_done);
-        }
-        if (it >= 1) {                                    // the stage of chunk it+2 is the stage of chunk it-1
-          const int sp = (it - 1) % TT_STAGES;
+        {  // MMAs of the last chunk: complete (acc_done waited), consume its stage barrier phase
+          const int sp = (total - 1) % TT_STAGES;
           mbar_wait(&mma_done[sp], (par_done >> sp) & 1u);
           par_done ^= 1u << sp;
         }
-        for (int q = 0; q < can_issue; ++q) issue(issued++);
-        if (do_drain) { drain(); chain = 0; } else { ++chain; }
+        cp_async_wait<0>();
+      } else {
+        // ---- MMA warp
+        int chain = 0;
+        for (int it = 0; it < total; ++it) {
+          const int s = it % TT_STAGES;
+          nbar_sync(TT_BAR_FULL0 + s, 256);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const bool do_drain = it == total - 1 || chain + 1 == TT_DRAIN;
+          if (lane == 0) {
+            const uint32_t ph = smem_u32(sm + s * TT_STAGE_BYTES), pl = ph + 2 * TT_PLANE;
+            const uint32_t qh = diag ? ph : ph + TT_PLANE, ql = diag ? pl : pl + TT_PLANE;
+            tt_mma_chunk(tmem_base, ph, pl, qh, ql, chain == 0);
+            umma_commit(&mma_done[s]);
+            if (do_drain) umma_commit(acc_done);
+          }
+          __syncwarp();
+          par_done ^= 1u << s;                              // bookkeeping: one phase of mma_done[s] per commit
+          if (do_drain) { drain(); chain = 0; } else { ++chain; }
+        }
       }
-      {  // MMAs of the last chunk: complete (acc_done waited), consume its stage barrier phase
-        const int sp = (total - 1) % TT_STAGES;
-        mbar_wait(&mma_done[sp], (par_done >> sp) & 1u);
-        par_done ^= 1u << sp;
-      }
-      cp_async_wait<0>();
       __syncthreads();
     }
     if (tr) tr[2] = gtime_ns();
@@ -1534,24 +1320,27 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
             v.y = (q0 + 1 <= R) ? creg[4 * j + 1] : 0.0f;
             v.z = (q0 + 2 <= R) ? creg[4 * j + 2] : 0.0f;
             v.w = (q0 + 3 <= R) ? creg[4 * j + 3] : 0.0f;
-            *reinterpret_cast<float4*>(mtile(Tt, tir, tk) + 4 * (R & 3)) = v;
+            *reinterpret_cast<float4*>(fi_row(Tt, tir, tk, R & 3)) = v;
           }
         }
       }
       __syncthreads();
       bool bad = false;
-      factor_invert_la(Tt, Ww, Pn, Wp, Dd, bad, tid);
+      factor_invert_la(Tt, Ww, Pn, Wp, Dd, bad, tid,
+                       (g.trace != nullptr && c == 1) ? reinterpret_cast<long long*>(g.trace + (int64_t)g.ntasks * 8) : nullptr);
       if (bad && g.status) atomicOr(g.status, LCB_ST_NOT_SPD);
       if (tr) tr[4] = gtime_ns();
-      {  // Linv(c) -> dinv[c] (row-major): thread = (row, half of the columns)
+      {  // Linv(c) -> dinv[c] hi / lo (row-major), a warp per row: coalesced 512-byte stores
         float* dv = g.dinv + (int64_t)c * NB * NB;
-        const int r = tid >> 1, hf = tid & 1, tir = r >> 2;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int tk = 16 * hf + j;
+        float* dvl = g.dinv_lo + (int64_t)c * NB * NB;
+        for (int idx = tid; idx < NB * 32; idx += 256) {
+          const int r = idx >> 5, tk = idx & 31, tir = r >> 2;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (tk <= tir) v = *reinterpret_cast<const float4*>(mtile(Ww, tir, tk) + 4 * (r & 3));
-          *reinterpret_cast<float4*>(dv + r * NB + 4 * tk) = v;
+          if (tk <= tir) v = *reinterpret_cast<const float4*>(fi_row(Ww, tir, tk, r & 3));
+          float4 h, l;
+          tt_split4(v, h, l);
+          *reinterpret_cast<float4*>(dv + r * NB + 4 * tk) = h;
+          *reinterpret_cast<float4*>(dvl + r * NB + 4 * tk) = l;
         }
       }
       __syncthreads();
@@ -1559,14 +1348,19 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
       if (tr) tr[5] = gtime_ns();
       if (g.with_inv) {  // Y(c, c) = Linv(c)^T
         float* Yt = g.Y + (int64_t)c * NB * g.ld + (int64_t)c * NB;
+        float* Ytl = g.Ylo + (int64_t)c * NB * g.ld + (int64_t)c * NB;
         const int r = tid & 127, ch = tid >> 7, tir = r >> 2;
         if (r < qrow_valid) {
 #pragma unroll 4
           for (int q = 0; q < 64; ++q) {
             const int cc = 64 * ch + q;
             if (cc < qrow_valid) {
-              const float v = ((cc >> 2) <= tir) ? mtile(Ww, tir, cc >> 2)[4 * (r & 3) + (cc & 3)] : 0.0f;
-              Yt[(int64_t)cc * g.ld + r] = v;
+              const float v = ((cc >> 2) <= tir) ? fi_row(Ww, tir, cc >> 2, r & 3)[cc & 3] : 0.0f;
+              uint32_t hb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+              const float h = __uint_as_float(hb);
+              Yt[(int64_t)cc * g.ld + r] = h;
+              Ytl[(int64_t)cc * g.ld + r] = __fsub_rn(v, h);
             }
           }
         }
@@ -1577,23 +1371,21 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
       continue;
     }
 
-    // ---------------- out = C Linv(c)^T : C hi / lo planes in stages 0 + 1 (A operand), Linv streamed through stage 2
+    // ---------------- out = C Linv(c)^T : C hi / lo planes (A operand, 128 KB) + the lower triangle of Linv hi / lo (80 KB:
+    // chunk ch of the reduction only meets output columns >= 32 ch, so only those rows of Linv are staged and the MMAs of
+    // chunk ch run with N = 128 - 32 ch)
     {
       uint8_t* Ch = sm;                         // 4 chunks hi (64 KB)
       uint8_t* Cl = sm + 4 * TT_PLANE;          // 4 chunks lo (64 KB)
-      uint8_t* Xh = sm + 8 * TT_PLANE;          // Linv: 2 chunks hi
-      uint8_t* Xl = sm + 10 * TT_PLANE;         //       2 chunks lo
+      uint8_t* Xh = sm + 8 * TT_PLANE;          // Linv hi: chunk ch at byte 128 * (128 ch - 16 ch (ch - 1)), rows >= 32 ch
+      uint8_t* Xl = Xh + TT_XPLANES;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = C0 + 4 * j;
         const int ch = col >> 5, kq = (col & 31) >> 2;
         const uint32_t off = (uint32_t)(ch * TT_PLANE + R * 128 + ((kq ^ (R & 7)) << 4));
         float4 h, l;
-        uint32_t b;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(creg[4 * j + 0])); h.x = __uint_as_float(b); l.x = __fsub_rn(creg[4 * j + 0], h.x);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(creg[4 * j + 1])); h.y = __uint_as_float(b); l.y = __fsub_rn(creg[4 * j + 1], h.y);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(creg[4 * j + 2])); h.z = __uint_as_float(b); l.z = __fsub_rn(creg[4 * j + 2], h.z);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(creg[4 * j + 3])); h.w = __uint_as_float(b); l.w = __fsub_rn(creg[4 * j + 3], h.w);
+        tt_split4(make_float4(creg[4 * j], creg[4 * j + 1], creg[4 * j + 2], creg[4 * j + 3]), h, l);
         *reinterpret_cast<float4*>(Ch + off) = h;
         *reinterpret_cast<float4*>(Cl + off) = l;
       }
@@ -1601,52 +1393,77 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
       if (tr) tr[3] = gtime_ns();
       __syncthreads();
       const float* dv = g.dinv + (int64_t)c * NB * NB;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        if (half == 1) {  // the MMAs of the first half read Xh / Xl: wait for them
-          mbar_wait(acc_done, par_acc);
-          par_acc ^= 1u;
-        }
-        tt_load_plane(Xh, dv, NB, (2 * half) * 32, NB, tid);
-        tt_load_plane(Xh + TT_PLANE, dv, NB, (2 * half + 1) * 32, NB, tid);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        tt_split(Xh, Xl, 2, tid);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        if (tid == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;");
+      const float* dvl = g.dinv_lo + (int64_t)c * NB * NB;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int ch = 2 * half + q;
-            tt_mma_chunk(tmem_base, smem_u32(Ch + ch * TT_PLANE), smem_u32(Cl + ch * TT_PLANE), smem_u32(Xh + q * TT_PLANE),
-                         smem_u32(Xl + q * TT_PLANE), ch == 0);
+      for (int ch = 0; ch < 4; ++ch) {
+        const int xo = 128 * (128 * ch - 16 * ch * (ch - 1));   // 0, 16 K, 28 K, 36 K
+        tt_load_plane<256>(Xh + xo, dv, NB, ch * 32, NB, tid, 32 * ch);
+        tt_load_plane<256>(Xl + xo, dvl, NB, ch * 32, NB, tid, 32 * ch);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int xo = 128 * (128 * ch - 16 * ch * (ch - 1));
+          const uint32_t ah = smem_u32(Ch + ch * TT_PLANE), al = smem_u32(Cl + ch * TT_PLANE);
+          const uint32_t bh = smem_u32(Xh + xo), bl = smem_u32(Xl + xo);
+          const uint32_t n = 128u - 32u * ch, td = tmem_base + 32u * ch;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ko = k * 32;
+            umma_tf32_n(td, tt_desc(al + ko), tt_desc(bh + ko), n, (ch == 0 && k == 0) ? 0u : 1u);
+            umma_tf32_n(td, tt_desc(ah + ko), tt_desc(bl + ko), n, 1u);
+            umma_tf32_n(td, tt_desc(ah + ko), tt_desc(bh + ko), n, 1u);
           }
-          umma_commit(acc_done);
         }
+        umma_commit(acc_done);
       }
       mbar_wait(acc_done, par_acc);
       par_acc ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;");
-      float* Ot = (isL ? g.A : g.Y) + ((int64_t)ti * NB + R) * g.ld + (int64_t)c * NB + C0;
-      const bool fullst = R < prow_valid && C0 + 64 <= qrow_valid;
+      // result -> shared memory (row stride 132 floats: conflict-free for one row per lane) -> coalesced hi / lo stores
+      float* Sh = reinterpret_cast<float*>(sm);
+      float* Sl = Sh + NB * 132;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
         tmem_ld32(tmem_mine + (uint32_t)(32 * hh), v);
-        if (fullst) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(Ot + 32 * hh + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else if (R < prow_valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (C0 + 32 * hh + j < qrow_valid) Ot[32 * hh + j] = v[j];
+        for (int j = 0; j < 8; ++j) {
+          float4 h, l;
+          tt_split4(make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), h, l);
+          *reinterpret_cast<float4*>(Sh + R * 132 + C0 + 32 * hh + 4 * j) = h;
+          *reinterpret_cast<float4*>(Sl + R * 132 + C0 + 32 * hh + 4 * j) = l;
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncthreads();
+      const int64_t ooff = (int64_t)ti * NB * g.ld + (int64_t)c * NB;
+      float* Ot = (isL ? g.A : g.Y) + ooff;
+      float* Otl = (isL ? g.Alo : g.Ylo) + ooff;
+      for (int idx = tid; idx < NB * 32; idx += 256) {
+        const int r = idx >> 5, q4 = idx & 31;
+        if (r < prow_valid) {
+          const float4 h = *reinterpret_cast<const float4*>(Sh + r * 132 + 4 * q4);
+          const float4 l = *reinterpret_cast<const float4*>(Sl + r * 132 + 4 * q4);
+          if (4 * q4 + 3 < qrow_valid) {
+            *reinterpret_cast<float4*>(Ot + (int64_t)r * g.ld + 4 * q4) = h;
+            *reinterpret_cast<float4*>(Otl + (int64_t)r * g.ld + 4 * q4) = l;
+          } else {
+            const float hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+            for (int e = 0; e < 4; ++e)
+              if (4 * q4 + e < qrow_valid) {
+                Ot[(int64_t)r * g.ld + 4 * q4 + e] = hv[e];
+                Otl[(int64_t)r * g.ld + 4 * q4 + e] = lv[e];
+              }
+          }
+        }
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -1665,14 +1482,15 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
 }
 
 // U[a][b] = (b >= a) ? Y[k-1-b][k-1-a] : 0     (Y = L^-T of the index-reversed matrix; U = J L^-1 J)
-__global__ void reverse_out_t_kernel(float* __restrict__ U, const float* __restrict__ Y, int64_t k) {
+__global__ void reverse_out_t_kernel(float* __restrict__ U, const float* __restrict__ Y, const float* __restrict__ Ylo,
+                                     int64_t k) {
   __shared__ float tile[32][33];
   const int64_t a0 = (int64_t)blockIdx.y * 32, b0 = (int64_t)blockIdx.x * 32;
   // U rows a0.., cols b0..  <-  Y rows k-1-b, cols k-1-a
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t b = b0 + r, a = a0 + threadIdx.x;       // read Y[k-1-b][k-1-a]: contiguous in a (descending)
     float v = 0.0f;
-    if (a < k && b < k && b >= a) v = Y[(k - 1 - b) * k + (k - 1 - a)];
+    if (a < k && b < k && b >= a) v = Y[(k - 1 - b) * k + (k - 1 - a)] + Ylo[(k - 1 - b) * k + (k - 1 - a)];
     tile[r][threadIdx.x] = v;                             // tile[b - b0][a - a0]
   }
   __syncthreads();
@@ -1711,12 +1529,12 @@ SideStreams* side_streams() {
   return &cache[dev];
 }
 
-constexpr int TILES_FULL_MAX = 4096;  // largest K factored by one chol_tiles_kernel launch (above: strips + tensor-core SYRK)
-static int tiles_mode() {             // LCB_CHOL_TILES=0: panel-launch chain, 2: SIMT tile kernel (A/B runs)
+constexpr int TILES_FULL_MAX = 16384;  // largest K factored by one chol_tiles_tc_kernel launch (above: the panel-launch chain)
+static int tiles_mode() {             // LCB_CHOL_TILES=0: panel-launch chain (A/B runs)
   static int m = -1;
   if (m < 0) {
     const char* e = getenv("LCB_CHOL_TILES");
-    m = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 1;
+    m = (e && e[0] == '0') ? 0 : 1;
   }
   return m;
 }
@@ -1724,17 +1542,30 @@ constexpr int SW = 512;        // super-panel width of the tensor-core path (Kd 
 constexpr int TRI_TG_MIN = 1024;  // trtri levels with node size >= this run on the tensor cores
 constexpr int TG_CHAIN = 256;     // accumulation chain length (columns) of the tensor-core contractions
 
+// tile-task path: A, Y, lo(A), lo(Y) [k, k] each; dinv hi / lo; flags + task counter; debug trace; diag sum
+static size_t tiles_flags_offset(int64_t k) { return (size_t)(4 * k * k) + (size_t)(2 * ceil_div(k, NB) * NB * NB); }
+static size_t tiles_trace_offset(int64_t k) {
+  const int64_t nblk = ceil_div(k, NB);
+  return tiles_flags_offset(k) + (size_t)((2 * nblk * nblk + 16 + 3) / 4 * 4);
+}
+constexpr size_t TILES_TRACE_EXTRA = 16 * 12 * 2 + 40 * 8 * 2;   // floats: the clock probes behind the task records
+static size_t tiles_ws_floats(int64_t k) {
+  const int64_t nblk = ceil_div(k, NB);
+  return tiles_trace_offset(k) + (size_t)(nblk * nblk * 16) + TILES_TRACE_EXTRA + 64;
+}
+
 static size_t chol_ws_floats(int64_t k) {
   const int64_t nblk = ceil_div(k, NB);
   const int64_t kp = ceil_div(k, 4) * 4;
   const size_t t_exact = (size_t)(k * k / 2 + k * NB);
   const size_t t_tg = (size_t)(9 * (kp / 2 + NB) * (kp / 2 + NB));  // planes of one trtri node
-  return (size_t)(k * k)                 // work matrix
+  const size_t chain = (size_t)(k * k)   // work matrix
          + std::max(t_exact, t_tg)       // T of the trtri recursion / operand planes
          + (size_t)(nblk * NB * NB)      // inverted diagonal blocks
          + (size_t)(4 * kp * NB)         // TRSM panel (exact path) / two sets of panel hi + lo planes
          + (size_t)(4 * kp * SW)         // two sets of hi / lo planes of a super-panel strip
          + 64;
+  return std::max(chain, tiles_ws_floats(k));
 }
 
 }  // namespace lcb
@@ -1744,12 +1575,7 @@ using namespace lcb;
 extern "C" size_t lcb_chol_ws_bytes(int64_t k) { return chol_ws_floats(k) * sizeof(float); }
 
 // debug aid (LCB_CHOL_TRACE=1): byte offset of the task trace inside the workspace (8 x u64 per task, nblk^2 tasks)
-extern "C" size_t lcb_chol_trace_offset(int64_t k) {
-  const int64_t nblk = ceil_div(k, NB);
-  const int64_t kp = ceil_div(k, 4) * 4;
-  const size_t t_floats = std::max((size_t)(k * k / 2 + k * NB), (size_t)(9 * (kp / 2 + NB) * (kp / 2 + NB)));
-  return ((size_t)(k * k) + t_floats + (size_t)(nblk * NB * NB) + (size_t)(4 * kp * NB)) * sizeof(float);
-}
+extern "C" size_t lcb_chol_trace_offset(int64_t k) { return tiles_trace_offset(k) * sizeof(float); }
 
 extern "C" int lcb_hessian_dead_fix(float* H, int64_t k, uint8_t* dead, void* stream) {
   LCB_REQUIRE(H != nullptr && k > 0, "lcb_hessian_dead_fix: bad arguments");
@@ -1776,7 +1602,9 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   float* strip = panel + 4 * kp * NB;         // planes [set][hi|lo][kp, SW]
   float* dsum = strip + 4 * kp * SW;
   const bool tg = gemm_mode() == 1 && k % 4 == 0 && tg_ok(ws, 4) && k > NB;
-  if (tg) LCB_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
+  const bool tiles = tg && k <= TILES_FULL_MAX && tiles_mode() != 0;
+  if (tiles) dsum = static_cast<float*>(ws) + tiles_ws_floats(k) - 64;
+  if (tg && !tiles) LCB_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
 
   diag_sum_kernel<<<1, 1024, 0, st>>>(H, k, dsum);
   LCB_LAUNCH_CHECK();
@@ -1784,31 +1612,28 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
   gather_reverse_damp_kernel<<<g2, 256, 0, st>>>(A, H, perm, k, damp, dsum);
   LCB_LAUNCH_CHECK();
 
-  if (tg && k <= TILES_FULL_MAX && tiles_mode() != 0) {
-    // ---- whole factorisation + triangular inverse as ONE persistent tile-task launch (exact fp32)
-    uint32_t* flags = reinterpret_cast<uint32_t*>(panel);
+  if (tiles) {
+    // ---- whole factorisation + triangular inverse as ONE persistent tile-task launch
+    float* w0 = static_cast<float*>(ws);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(w0 + tiles_flags_offset(k));
     const size_t nfl = (size_t)(2 * nblk * nblk + 16);
     LCB_CUDA(cudaMemsetAsync(flags, 0, nfl * sizeof(uint32_t), st));
     TileArgs ta{};
-    ta.A = A; ta.Y = T; ta.dinv = dinv_all;
+    ta.A = A; ta.Y = w0 + k * k; ta.Alo = w0 + 2 * k * k; ta.Ylo = w0 + 3 * k * k;
+    ta.dinv = w0 + 4 * k * k; ta.dinv_lo = ta.dinv + nblk * NB * NB;
     ta.flagL = flags; ta.flagY = flags + nblk * nblk; ta.counter = flags + 2 * nblk * nblk;
     ta.status = status; ta.ld = k; ta.k = (int)k; ta.nblk = (int)nblk; ta.c0 = 0; ta.c1 = (int)nblk; ta.with_inv = 1;
     ta.ntasks = (int)(nblk * nblk);
     if (getenv("LCB_CHOL_TRACE")) {  // debug: task trace at byte offset lcb_chol_trace_offset(k) of the workspace
-      ta.trace = reinterpret_cast<unsigned long long*>(strip);
-      LCB_CUDA(cudaMemsetAsync(strip, 0, (size_t)ta.ntasks * 64, st));
+      ta.trace = reinterpret_cast<unsigned long long*>(w0 + tiles_trace_offset(k));
+      LCB_CUDA(cudaMemsetAsync(ta.trace, 0, ((size_t)ta.ntasks * 16 + TILES_TRACE_EXTRA) * sizeof(float), st));
     }
     const unsigned grid = (unsigned)std::min<int64_t>(ta.ntasks, sm_count());
-    if (tiles_mode() == 2) {  // fp32 SIMT tile products (A/B runs)
-      LCB_CUDA(cudaFuncSetAttribute(chol_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
-      chol_tiles_kernel<<<grid, 256, CT_SMEM, st>>>(ta);
-    } else {
-      LCB_CUDA(cudaFuncSetAttribute(chol_tiles_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
-      chol_tiles_tc_kernel<<<grid, 256, TT_SMEM, st>>>(ta);
-    }
+    LCB_CUDA(cudaFuncSetAttribute(chol_tiles_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
+    chol_tiles_tc_kernel<<<grid, 256, TT_SMEM, st>>>(ta);
     LCB_LAUNCH_CHECK();
     dim3 gr((unsigned)ceil_div(k, 32), (unsigned)ceil_div(k, 32));
-    reverse_out_t_kernel<<<gr, dim3(32, 8), 0, st>>>(U, T, k);
+    reverse_out_t_kernel<<<gr, dim3(32, 8), 0, st>>>(U, ta.Y, ta.Ylo, k);
     LCB_LAUNCH_CHECK();
     return LCB_OK;
   }

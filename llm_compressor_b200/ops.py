@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .quantizers import _ptr, _status_word, _stream
+from .quantizers import DeferredStatus, _ptr, _status_word, _stream
 
 
 def _need_cuda(*ts):
@@ -154,10 +154,44 @@ def dead_fix(H):
     return dead.bool()
 
 
-def chol_inv_upper(H, perm=None, percdamp=0.01, out=None):
+class PendingFactor:
+    """Outcome of a deferred lcb_chol_inv_upper: `resolve()` returns False when the factorisation succeeded and True
+    when it had to be redone with the reference's second, larger damping (U was overwritten: dependents must be
+    recomputed); raises like torch.linalg.cholesky when that fails too (ref: gptq/core.py:213-221)."""
+
+    def __init__(self, st, src, U, perm, percdamp, ws, ws_bytes):
+        self.st, self.src, self.U, self.perm, self.percdamp, self.ws, self.ws_bytes = st, src, U, perm, percdamp, ws, ws_bytes
+        self._done = None
+
+    def resolve(self):
+        if self._done is None:
+            self._done = False
+            if self.st.value() & _lib.ST_NOT_SPD:
+                _chol_call(self.src, self.U, self.perm, self.percdamp * (11.0 + 10.0 * self.percdamp), self.ws, self.ws_bytes,
+                           check=True)
+                self._done = True
+            self.src = self.ws = None
+        return self._done
+
+
+def _chol_call(src, U, perm, damp, ws, ws_bytes, check):
+    st = DeferredStatus(src.device)
+    with torch.cuda.device(src.device):
+        rc = _lib.lib().lcb_chol_inv_upper(_ptr(src), _ptr(U), src.shape[0], _ptr(perm), float(damp), _ptr(ws), ws_bytes,
+                                           _ptr(st.word), _stream(src.device))
+    _lib.check(rc, "lcb_chol_inv_upper")
+    st.arm()
+    if check and (st.value() & _lib.ST_NOT_SPD):
+        raise RuntimeError("linalg.cholesky: the Hessian is not positive-definite even after 10x damping")
+    return st
+
+
+def chol_inv_upper(H, perm=None, percdamp=0.01, out=None, defer=False):
     """U with (H[perm][:, perm] + damp*mean(diag)*I)^-1 = U^T U, including the reference's retry
     with 10x damping on a failed factorisation (ref: gptq/core.py:207-224).  H is not modified
-    unless `out is H`."""
+    unless `out is H`.
+    defer=True returns (U, PendingFactor): the status word is read back without draining the stream -- enqueue the
+    work that depends on U, then call `.resolve()`; it reports whether the retry had to run (rare)."""
     _need_cuda(H, perm)
     L = _lib.lib()
     k = H.shape[0]
@@ -167,22 +201,15 @@ def chol_inv_upper(H, perm=None, percdamp=0.01, out=None):
     U = out if out is not None else torch.empty_like(H)
     ws_bytes = L.lcb_chol_ws_bytes(k)
     ws = _ws(ws_bytes, H.device)
-    status = _status_word(H.device)
     src = H
     if U.data_ptr() == H.data_ptr():
         src = H.clone()  # keep the input for a possible retry
-    for damp in (percdamp, percdamp * (11.0 + 10.0 * percdamp)):
-        # second value == the reference's "damp again by 10x on the already damped H"
-        with torch.cuda.device(H.device):
-            rc = L.lcb_chol_inv_upper(_ptr(src), _ptr(U), k, _ptr(perm), float(damp), _ptr(ws), ws_bytes,
-                                         _ptr(status), _stream(H.device))
-        _lib.check(rc, "lcb_chol_inv_upper")
-        st = int(status.item())
-        if st:
-            status.zero_()
-        if not (st & _lib.ST_NOT_SPD):
-            return U
-    raise RuntimeError("linalg.cholesky: the Hessian is not positive-definite even after 10x damping")
+    st = _chol_call(src, U, perm, percdamp, ws, ws_bytes, check=False)
+    pending = PendingFactor(st, src, U, perm, percdamp, ws, ws_bytes)
+    if defer:
+        return U, pending
+    pending.resolve()
+    return U
 
 
 def gptq_block_update(cfg, W, U, scales, zeros, keep, group, P=None, block=128):

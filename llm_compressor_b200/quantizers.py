@@ -72,6 +72,41 @@ def _status_word(device):
     return t
 
 
+class DeferredStatus:
+    """A device status word (LCB_ST_* bits) whose read-back does not drain the stream.
+
+    The reference reads its error conditions synchronously (`assert not torch.isnan(scales).any()` int_quant.py:165;
+    `torch.linalg.cholesky` raising, gptq/core.py:213-221).  Here the producing call gets a private word; `arm()`
+    copies it to a pooled pinned host word on the current stream and records an event; `value()` waits for THAT event
+    only, so work enqueued after `arm()` keeps the GPU busy while the host looks at the result."""
+    _pool = {}
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        free = DeferredStatus._pool.setdefault((self.device.type, self.device.index), [])
+        if free:
+            self.word, self.host, self.event = free.pop()
+        else:
+            self.word = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self.event = torch.cuda.Event()
+        self.word.zero_()
+        self._value = None
+
+    def arm(self):
+        self.host.copy_(self.word, non_blocking=True)
+        self.event.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def value(self):
+        if self._value is None:
+            self.event.synchronize()
+            self._value = int(self.host[0])
+            DeferredStatus._pool[(self.device.type, self.device.index)].append((self.word, self.host, self.event))
+            self.word = self.host = self.event = None
+        return self._value
+
+
 def _dt(x):
     if x.dtype == torch.bfloat16:
         return _lib.BF16
@@ -96,7 +131,7 @@ def _prod(xs):
 
 
 def qdq_raw(cfg, x, axis, group, find, apply, scales=None, zeros=None, codes=False, nv_amax=None, check_nan=True,
-            blocked=False):
+            blocked=False, status=None):
     """One lcb_qdq call on a CUDA tensor.  Returns (out, scales, zeros, codes).
 
     Geometry (not blocked): axis -1 -> rows = prod(shape[:-1]), cols = shape[-1];
@@ -141,13 +176,19 @@ def qdq_raw(cfg, x, axis, group, find, apply, scales=None, zeros=None, codes=Fal
     cds = torch.empty(shape, dtype=torch.uint8, device=x.device) if (codes and apply) else None
     ws_bytes = L.lcb_qdq_ws_bytes(ctypes.byref(cfg), dt, batch, rows, cols, axis, group)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    status = _status_word(x.device) if (find and check_nan) else None
+    deferred = status       # a DeferredStatus: the caller checks the NaN-scale bit later (no host sync here)
+    if deferred is not None:
+        status = deferred.word if find else None
+    else:
+        status = _status_word(x.device) if (find and check_nan) else None
     mode = (_lib.QDQ_FIND if find else 0) | (_lib.QDQ_APPLY if apply else 0)
     with torch.cuda.device(x.device):
         rc = L.lcb_qdq(ctypes.byref(cfg), dt, mode, _ptr(x), _ptr(out), batch, rows, cols, axis, group, _ptr(scales),
                        _ptr(zeros), _ptr(cds), _ptr(nv_amax), _ptr(ws), ws_bytes, _ptr(status), _stream(x.device))
     _lib.check(rc, "lcb_qdq")
-    if status is not None:
+    if deferred is not None:
+        deferred.arm()
+    elif status is not None:
         st = int(status.item())  # same host sync as the reference's assert (int_quant.py:165)
         if st:
             status.zero_()
@@ -204,11 +245,12 @@ class BaseQuantizer(nn.Module):  # ref: quantizers/base.py:8
         kernel refuses the rest (LCB_ERR_UNSUPPORTED)."""
         return bool(self.mse)
 
-    def find_params(self, x, already_reshaped=False):
+    def find_params(self, x, already_reshaped=False, status=None):
+        """`status` (extension): a DeferredStatus that receives the NaN-scale bit instead of the synchronous assert."""
         if self.group_size != 0 and not already_reshaped:
             self._resolve_group(x)
         _, s, z, _ = qdq_raw(self._cfg(self._mse()), x, self.axes, self.group_size, True, False, check_nan=self.check_nan,
-                             blocked=bool(already_reshaped and self.group_size != 0))
+                             blocked=bool(already_reshaped and self.group_size != 0), status=status)
         return s, z
 
     def forward(self, x, **kwargs):

@@ -13,7 +13,8 @@ arithmetic stage runs in liblcb200.so through llm_compressor_b200.ops.
 import torch
 import torch.nn as nn
 
-from . import ops, parallel
+from . import _lib, ops, parallel
+from .quantizers import DeferredStatus
 
 
 def _is_conv1d(layer):
@@ -85,9 +86,22 @@ class Factor:
     H, so a driver may compute one Factor per group and reuse it (the reference recomputes it per
     Linear from identical copies, ref: gptq/core.py:121-137; gptaq shares H the same way, :143-159)."""
 
-    def __init__(self, dead, perm, invperm, col_perm, U, P, group_size):
+    def __init__(self, dead, perm, invperm, col_perm, U, P, group_size, pending=None, p_args=None):
         self.dead, self.perm, self.invperm, self.col_perm = dead, perm, invperm, col_perm
         self.U, self.P, self.group_size = U, P, group_size
+        self._pending, self._p_args = pending, p_args
+
+    def resolve(self):
+        """Deferred outcome of the factorisation (ops.PendingFactor): True when U had to be recomputed with the
+        reference's 10x damping retry -- whatever was solved with the first U must be solved again."""
+        if self._pending is None:
+            return False
+        redone = self._pending.resolve()
+        self._pending = None
+        if redone and self._p_args is not None:
+            self.P = ops.gptaq_p(self._p_args[0], self.U, self._p_args[1])
+        self._p_args = None
+        return redone
 
 
 def factorize(H, group_size, actorder=True, percdamp=0.01, dXXT=None, alpha=0.25):
@@ -109,13 +123,14 @@ def factorize(H, group_size, actorder=True, percdamp=0.01, dXXT=None, alpha=0.25
             perm = torch.argsort(diag.reshape(-1, group_size).sum(-1), descending=True)
             col_perm = (perm.unsqueeze(1) * group_size + torch.arange(group_size, device=perm.device)).reshape(-1)
         invperm = torch.argsort(perm)
-    U = ops.chol_inv_upper(H, perm=col_perm, percdamp=percdamp)
-    P = None
+    U, pending = ops.chol_inv_upper(H, perm=col_perm, percdamp=percdamp, defer=True)
+    P = p_args = None
     if dXXT is not None:
         if col_perm is not None:
             dXXT = dXXT[col_perm][:, col_perm].contiguous()
         P = ops.gptaq_p(dXXT, U, alpha)
-    return Factor(dead, perm, invperm, col_perm, U, P, group_size)
+        p_args = (dXXT, alpha)
+    return Factor(dead, perm, invperm, col_perm, U, P, group_size, pending, p_args)
 
 
 def _solve(q, W, factor, block_size):
@@ -129,7 +144,8 @@ def _solve(q, W, factor, block_size):
     # per-column branch: the reference takes the per-row parameters before the permutation (ref :179-185); row
     # max / min do not depend on the column order, so the permuted matrix gives the same values.  Grouped branch:
     # static groups of the re-ordered W (ref :198).
-    scales, zeros = q.find_params(Wp)
+    nan_st = DeferredStatus(Wp.device) if getattr(q, "check_nan", True) else None
+    scales, zeros = q.find_params(Wp, status=nan_st) if nan_st is not None else q.find_params(Wp)
     if per_col:
         s2 = scales.float().reshape(-1, 1).expand(N, 1).contiguous()
         z2 = zeros.float().reshape(-1, 1).expand(N, 1).contiguous()
@@ -140,7 +156,13 @@ def _solve(q, W, factor, block_size):
         grp = group_size
     Q = ops.gptq_block_update(q._cfg(), Wp, factor.U, s2, z2, keep, grp, P=factor.P, block=block_size)
     # inverse permutation + cast back to the weight dtype (ref :267-278)
-    return ops.gptq_scatter(Q, factor.col_perm, W.dtype)
+    out = ops.gptq_scatter(Q, factor.col_perm, W.dtype)
+    # the two error conditions the reference reads synchronously, looked at AFTER the solve has been enqueued
+    if nan_st is not None:
+        assert not (nan_st.value() & _lib.ST_NAN_SCALE), "NaN in quantization scales"
+    if factor.resolve():   # not positive definite at 1 % damping: U was redone with the 10x retry (ref: gptq/core.py:216-221)
+        return _solve(q, W, factor, block_size)
+    return out
 
 
 def _layer_w(layer):

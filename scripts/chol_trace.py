@@ -45,3 +45,9 @@ if ys:
     for x in ys:
         if x[2] == nblk - 1 and x[1] in (0, nblk // 2, nblk - 2):
             print("  Y(%d,%d) fetch %.1f acc %.1f diagflag %.1f end %.1f" % (x[1], x[2], x[3], x[4], x[5], x[7]))
+# per-step clock64 probes inside factor_invert_la of diagonal task c = 1 (cycles, relative to step 0 start)
+dbg = ws[off + nblk * nblk * 64: off + nblk * nblk * 64 + 16 * 12 * 8].cpu().numpy().view(np.int64).reshape(16, 12)
+b0 = dbg[0, 0]
+print("step: chain[P1start P1end P3Async LAend] worker0[P1sync P2Wend LAsync first P3end barW]  (cycles since step-0 start)")
+for p in range(16):
+    print("  p=%2d " % p + " ".join("%7d" % (int(v - b0) if v else -1) for v in dbg[p, :10]))
