@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY. Import shim for the reference (pjh5672/llm-compressor at /root/reference).
 
-Only usable in the build container, where /root/reference is mounted. It is used by
-oracle/gen_golden.py to produce tests/golden/*.npz and by the (container-only) cross-checks of
-the oracle restatement.  Nothing in the product package, the -m gpu tests, smoke() or bench.py
-imports this file.
+Imports the reference from /root/reference (build container) or from the unmodified copy in oracle/_ref/
+(GPU box; see oracle/make_ref.py).  Used by oracle/gen_golden*.py to produce tests/golden/*.npz, by the
+cross-checks of the oracle restatement, by bench.py's reference legs (`--impl reference`, `reference_eager_b200`:
+the reference timed as the baseline, never as the product) and by tests/test_reference_dropin_gpu.py.  Nothing in
+the product package imports this file.
 
 The stubs replace import-time-only dependencies of the reference that are absent here
 (ref: llm_compressor/utils/general.py:10 matplotlib; utils/parser.py:4 easydict;
@@ -14,7 +15,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("LC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the unmodified copy that oracle/make_ref.py left in
+    oracle/_ref/ (git-ignored, travels with the snapshot)."""
+    for cand in (os.environ.get("LC_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "llm_compressor")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _default_root()
 
 
 def available():
