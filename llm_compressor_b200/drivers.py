@@ -46,6 +46,12 @@ class _Catcher(nn.Module):
 def _catch_inputs(model, device, dataloader):
     layers = model.get_layers()
     inps, layer_kwargs = [], {}
+    dt = next(layers[0].parameters()).dtype
+    if dt != torch.bfloat16:
+        # the calibration kernels take bf16 activations (exact bf16 x bf16 products on the tensor cores); the reference's
+        # hooks upcast whatever comes with x.float().  Fail before any calibration work rather than in the first hook.
+        raise NotImplementedError("llm_compressor_b200 drivers calibrate bfloat16 models only (got %s): load the checkpoint "
+                                  "with torch_dtype=torch.bfloat16" % dt)
     layers[0] = layers[0].to(device)
     model.move_embed(device)
     layers[0] = _Catcher(layers[0], inps, layer_kwargs)
@@ -62,7 +68,9 @@ def _catch_inputs(model, device, dataloader):
 
 
 def _first(out):
-    return out[0] if isinstance(out, (tuple, list)) else out[0]
+    """layer(x)[0] as the reference writes it (gptq/core.py:140): the hidden states of a tuple, or -- transformers 5.x
+    layers return a tensor -- its single batch entry."""
+    return out[0]
 
 
 def _default_loader(model, n_samples, seq_len, dataloader):
@@ -167,13 +175,19 @@ def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, da
             for name in subset:
                 wq = subset[name].weight_quantizer
                 wq.mse = mse
+                # the Factor depends on the group size only (act-order granularity); within one Factor,
+                # update_weights_shared stacks just the Linears whose quantizers agree completely (solvers.quantizer_key)
                 key = wq.group_size if wq.group_size not in (0, -1) else -1
                 by_group.setdefault(key, []).append(name)
             for key, members in by_group.items():
                 gs = subset[members[0]].weight_quantizer.group_size
                 factor = solvers.factorize(H, gs, actorder=True, percdamp=0.01)
-                # one stacked [sum N, K] solve for the Linears that share this factor
-                solvers.update_weights_shared([subset[n] for n in members], device, factor, block_size=128)
+                # one stacked [sum N, K] solve per set of identically configured Linears that share this factor
+                by_q = {}
+                for n in members:
+                    by_q.setdefault(solvers.quantizer_key(subset[n].weight_quantizer), []).append(n)
+                for same in by_q.values():
+                    solvers.update_weights_shared([subset[n] for n in same], device, factor, block_size=128)
                 del factor
             for name in subset:
                 del subset[name].weight_quantizer

@@ -8,8 +8,9 @@ quantizers/int_quant.py:210-212 and utils.py:263-272).
 Codes and scales come from the same lcb_qdq call that produces the fake-quantised tensor, so "integer codes
 bit-exact" is checkable from the outside.  Scale storage: INT / FP keep the quantizer's scale and zero-point tensors
 (weight dtype); MX stores the shared exponent as one E8M0 byte per block when the scale is a power of two (it is unless
-the reference's clamp(min=1e-5) hit, mx_quant.py:151 -- those blobs keep the full scale); NVFP stores the per-block
-scale as fp8-e4m3 bytes relative to the fp32 per-matrix scale (nvfp_quant.py:87-100) under the same proviso.
+the reference's clamp(min=1e-5) hit, mx_quant.py:151 -- those blobs keep the full scale); NVFP keeps the quantizer's
+per-block scale tensor (weight dtype: the product s8 * s32 of nvfp_quant.py:87-100, already clamped) -- storing the
+e4m3 factor and the fp32 per-matrix factor separately would not reproduce the clamp(min=1e-5) cases.
 Decoding (`unpack_weight`) is plain torch arithmetic in the weight dtype, op for op the reference's `(q - z) * s` /
 `q * s + z`; it is the checker of the format, not a hot path.
 """
@@ -52,6 +53,9 @@ def _is_four_bit(q):
 def pack_weight(W, quantizer):
     """Quantise W [N, K] with `quantizer` (an llm_compressor_b200 quantizer, axes = -1) and return the packed blob."""
     assert W.dim() == 2 and quantizer.axes == -1
+    if quantizer.group_size == 0:
+        raise NotImplementedError("pack_weight: per-tensor scaling (group_size 0) has no per-row scale layout; use a per-row "
+                                  "(-1) or grouped quantizer")
     dq, scales, zeros, codes = quantizer.quantize_with_codes(W)
     kind = ("nvfp" if isinstance(quantizer, NVFPQuantizer) else "mx" if isinstance(quantizer, MXQuantizer)
             else "int" if isinstance(quantizer, INTQuantizer) else "fp")
@@ -89,6 +93,10 @@ def unpack_weight(blob):
     s = s.reshape(n, G, 1).to(dt)
     if fmt.startswith("int"):
         q = codes.view(torch.int8).reshape(n, k).to(dt)
+        if kind in ("mx", "nvfp"):
+            # MX / NVFP element type int4 / int8 is a FIXED-POINT value: the code is q * 2^(mbits - 2) (qmath.cuh encode_code,
+            # ref: utils.py:263-268 with ebits == 0), i.e. int4 codes are in units of 1/4 and int8 codes in units of 1/64
+            q = q / (4.0 if fmt == "int4" else 64.0)
     elif fmt == "fp4_e2m1":
         lut = torch.tensor(_FP4_LUT, dtype=torch.float32, device=dev)
         c = codes.reshape(n, k).long()

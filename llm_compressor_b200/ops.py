@@ -28,7 +28,10 @@ def _x2d(x):
     batch = x.shape[0]
     x2 = x.reshape(-1, x.shape[-1])
     if x2.dtype != torch.bfloat16:
-        raise NotImplementedError("calibration activations must be bfloat16 (got %s)" % x2.dtype)
+        # the tcgen05 Hessian kernel multiplies bf16 operands exactly; fp16 / fp32 activations would need a hi + lo split
+        # (four Gram products) that is not built -- fail loudly instead of rounding the activations to bf16
+        raise NotImplementedError("calibration activations must be bfloat16 (got %s): load the model in bf16 "
+                                  "(drivers check this before calibration starts)" % x2.dtype)
     return x2.contiguous(), batch
 
 
@@ -89,6 +92,7 @@ class HessianAccumulator:
     def __init__(self, H, defer=4):
         self.H, self.defer, self.n = H, max(1, min(int(defer), MAX_DEFER)), 0
         self._pending = []
+        self._versions = []
 
     def add(self, x):
         x2d, batch = _x2d(x)
@@ -96,6 +100,7 @@ class HessianAccumulator:
         if self._pending and self._pending[0].shape != x2d.shape:
             self._launch()
         self._pending.append(x2d)
+        self._versions.append(x2d._version)
         if len(self._pending) >= self.defer:
             self._launch()
         return self.n
@@ -104,7 +109,12 @@ class HessianAccumulator:
         xs = self._pending
         if not xs:
             return
+        for t, v in zip(xs, self._versions):
+            if t._version != v:   # deferred inputs are held by reference: an in-place write since add() would corrupt H silently
+                raise RuntimeError("HessianAccumulator: a deferred hook input was modified in place before the launch "
+                                   "(use HESSIAN_DEFER = 1 for models that overwrite activations in place)")
         self._pending = []
+        self._versions = []
         H = self.H
         _need_cuda(H, *xs)
         tokens, k = xs[0].shape

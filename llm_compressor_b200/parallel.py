@@ -162,6 +162,14 @@ def sparsegpt_update_sharded(W_local, U, sparsity, block=128, group=None):
     if w == 1:
         return ops.sparsegpt_update(W_local, U, sparsity, block)
     n_total = _total(W_local.shape[0], W_local.device, group)
+    if W_local.shape[0] == 0:
+        # an empty row shard (ceil-divided shards: trailing ranks can be empty) still takes part in every collective of
+        # the loop -- 4 histogram all-reduces per 128-column block -- with zero counts, or the other ranks would block
+        zero = torch.zeros(256, dtype=torch.int32, device=U.device)
+        for _ in range(4 * ((U.shape[0] + block - 1) // block)):
+            zero.zero_()
+            dist.all_reduce(zero, op=dist.ReduceOp.SUM, group=group)
+        return W_local
     return ops.sparsegpt_update(W_local, U, sparsity, block, n_total=n_total,
                                 reduce=lambda hist: dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group))
 

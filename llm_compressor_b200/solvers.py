@@ -192,6 +192,12 @@ def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, fa
     _store_w(layer, _solve(q, W, factor, block_size))
 
 
+def quantizer_key(q):
+    """Everything of a weight quantizer that changes the solve's result (used to decide what may share a stacked solve)."""
+    return (type(q).__name__, getattr(q.format, "name", str(q.format)), q.group_size, q.axes, bool(q.zero_point),
+            int(getattr(q, "scale_ebits", 8)), bool(getattr(q, "mse", False)))
+
+
 def update_weights_shared(layers, device, factor, block_size=128):
     """Solve several Linears that share one Factor (q/k/v, gate/up: same input, same H) as ONE stacked
     [sum N_i, K] problem.  Rows are independent given U, the permutation and row-wise quantiser
@@ -200,8 +206,12 @@ def update_weights_shared(layers, device, factor, block_size=128):
     Quantisers with a per-matrix statistic (NVFP's global amax, per-tensor scales) are not stacked."""
     layers = list(layers)
     q0 = layers[0].weight_quantizer
+    # one stacked solve runs q0's find_params / format for every row: only Linears whose quantizers agree in EVERYTHING
+    # that shapes the result may be stacked (the reference supports per-layer mixed precision, e.g. int4 q_proj next to
+    # int8 k_proj at the same group size: parser.py register_4_to_8bit_config); the others are solved one by one with
+    # the shared Factor, each with its own quantizer as the reference does (gptq/core.py:129-137).
     stackable = len(layers) > 1 and type(q0).__name__ != "NVFPQuantizer" and q0.group_size != 0 and q0.axes == -1 \
-        and not any(_is_conv1d(l) for l in layers) and all(type(l.weight_quantizer) is type(q0) for l in layers)
+        and not any(_is_conv1d(l) for l in layers) and all(quantizer_key(l.weight_quantizer) == quantizer_key(q0) for l in layers)
     if not stackable:
         for l in layers:
             _update_weight(l, device, block_size, 0.01, True, factor=factor)

@@ -39,11 +39,25 @@ class _Block(nn.Module):
         return (x,)
 
 
-def build_model(N, K, weight="int4-g[128]-rw", act_in=None, dtype=torch.bfloat16, seed=0, W=None):
+def build_model(N, K, weight="int4-g[128]-rw", act_in=None, dtype=torch.bfloat16, seed=0, W=None, fake_quantizer=None):
+    """`fake_quantizer`: a replacement for the reference's FakeQuantizer factory (quant.py:36-63) that the reference's own
+    QLinear then calls (modules/qlinear.py:41-55) -- the first of the three swaps of INTEGRATION.md section 2."""
     ref_shim.install()
     import llm_compressor.quantization.calibrations.gptq.core as G  # noqa: F401  (installs the sys.path hack first)
+    import llm_compressor.modules.qlinear as QL
     from llm_compressor.modules.qlinear import QLinear
     from llm_compressor.utils.parser import QuantConfigParser
+
+    saved_fq = QL.FakeQuantizer
+    if fake_quantizer is not None:
+        QL.FakeQuantizer = fake_quantizer
+    try:
+        return _build_model(QLinear, QuantConfigParser, N, K, weight, act_in, dtype, seed, W)
+    finally:
+        QL.FakeQuantizer = saved_fq
+
+
+def _build_model(QLinear, QuantConfigParser, N, K, weight, act_in, dtype, seed, W):
 
     qc = QuantConfigParser().build_cfg(weight, act_in, None, None)
     g = torch.Generator().manual_seed(seed)
@@ -69,16 +83,31 @@ def build_model(N, K, weight="int4-g[128]-rw", act_in=None, dtype=torch.bfloat16
     return m
 
 
-def run_gptq(N, K, n_samples, seq_len, device, weight="int4-g[128]-rw", seed=0, patch=None, W=None):
+def run_rtn(N, K, device, weight="int4-g[128]-zp-rw", seed=0, W=None, fake_quantizer=None):
+    """The reference's rtn() driver (rtn/core.py:16-61), unmodified, on the duck model; returns the model."""
+    ref_shim.install()
+    import llm_compressor.quantization.calibrations.gptq.core as G  # noqa: F401
+    import llm_compressor.quantization.calibrations.rtn.core as RTN
+
+    model = build_model(N, K, weight, seed=seed, W=W, fake_quantizer=fake_quantizer)
+    with torch.no_grad():
+        RTN.rtn(model, torch.device(device), False, False)
+    return model
+
+
+def run_gptq(N, K, n_samples, seq_len, device, weight="int4-g[128]-rw", seed=0, patch=None, W=None, fake_quantizer=None,
+             hook_override=None):
     """One call of the reference's gptq() on the duck model.  Returns (model, hook seconds per call, update_weight seconds).
-    `patch(G)` may swap reference globals before the call (the drop-in test swaps in this repository's objects)."""
+    The drop-in test swaps in this repository's objects, as INTEGRATION.md section 2 tells a maintainer to:
+    `fake_quantizer` replaces the FakeQuantizer factory, `patch(G)` may replace reference globals (G.update_weight),
+    `hook_override` stands in for the body of the forward-hook closure (gptq/core.py:103-119 is local to gptq())."""
     ref_shim.install()
     import llm_compressor.quantization.calibrations.gptq.core as G
 
     dev = torch.device(device)
     cuda = dev.type == "cuda"
     sync = torch.cuda.synchronize if cuda else (lambda: None)
-    model = build_model(N, K, weight, seed=seed, W=W)
+    model = build_model(N, K, weight, seed=seed, W=W, fake_quantizer=fake_quantizer)
     loader = [(torch.randint(0, VOCAB, (1, seq_len), generator=torch.Generator().manual_seed(seed + i)), None)
               for i in range(n_samples)]
     saved = dict(get_loaders=G.get_loaders, update_weight=G.update_weight, reg=nn.Module.register_forward_hook)
@@ -97,6 +126,9 @@ def run_gptq(N, K, n_samples, seq_len, device, weight="int4-g[128]-rw", seed=0, 
         return r
 
     def reg(self, hook, *a, **k):
+        if hook_override is not None:
+            hook = hook_override
+
         def timed_hook(mod, x, y):
             sync()
             t0 = time.perf_counter()

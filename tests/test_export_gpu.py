@@ -32,7 +32,9 @@ def test_pack4_unpack4_round_trip(numel):
 
 CASES = [("int", "int4", 128, False), ("int", "int4", 128, True), ("int", "int8", -1, True), ("int", "int4", -1, False),
          ("fp", "fp8_e4m3", -1, False), ("fp", "fp4_e2m1", 128, True), ("mx", "fp4_e2m1", 32, False),
-         ("mx", "fp8_e4m3", 32, False), ("nvfp", "fp4_e2m1", 16, False)]
+         ("mx", "fp8_e4m3", 32, False), ("nvfp", "fp4_e2m1", 16, False),
+         # MX with fixed-point int elements: codes are in units of 2^-(mbits-2) (unpack decoded them 4x / 64x too large)
+         ("mx", "int4", 32, False), ("mx", "int8", 32, False)]
 
 
 @pytest.mark.parametrize("t,f,g,zp", CASES, ids=["%s-%s-g%d%s" % (t, f, g, "-zp" if zp else "") for t, f, g, zp in CASES])
@@ -58,3 +60,10 @@ def test_packed_blob_decodes_to_the_fake_quantised_weight(t, f, g, zp, dtype):
         blob2, dq2 = export.pack_weight(W2, _q(t, f, g, zp))
         assert blob2["scales"] is None and blob2["scales_e8m0"].dtype == torch.uint8
         assert torch.equal(export.unpack_weight(blob2), dq2)
+
+
+def test_per_tensor_quantizer_is_rejected_not_divided_by_zero():
+    from llm_compressor_b200 import export
+    W = torch.zeros(8, 128, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(NotImplementedError):
+        export.pack_weight(W, _q("int", "int8", 0, False))

@@ -1,0 +1,67 @@
+"""Drop-in boundary proof: the reference's OWN drivers -- `rtn()` and `gptq()`,
+unmodified, imported from oracle/_ref (the git-ignored copy made by oracle/make_ref.py; /root/reference in the build
+container) -- run with this repository's objects swapped into the reference's namespaces exactly where a maintainer would
+put them:
+    llm_compressor.modules.qlinear.FakeQuantizer          <- llm_compressor_b200.FakeQuantizer        (factory, quant.py:36-63)
+    gptq.core.update_weight                               <- llm_compressor_b200.solvers.update_weight (core.py:163-281)
+    the forward-hook closure of gptq() (core.py:103-119)  <- llm_compressor_b200.solvers.cache_hessian_weight
+and are compared with the same drivers running entirely on the reference's code (PyTorch eager on the same GPU)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_timing  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_timing.available(), reason="no reference copy (oracle/_ref) on this box")]
+DEV = "cuda:0"
+
+
+def _w(N, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (0.02 * torch.randn(N, K, generator=g)).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("weight", ["int4-g[128]-zp-rw", "int8-g[-1]-rw", "nvfp4_e2m1-g[16]-rw", "mxfp4_e2m1-g[32]-rw"])
+def test_reference_rtn_with_swapped_fake_quantizer_is_bit_exact(weight):
+    import llm_compressor_b200 as lc
+    W = _w(768, 1024, 3)
+    ref = ref_timing.run_rtn(768, 1024, DEV, weight=weight, W=W)
+    ours = ref_timing.run_rtn(768, 1024, DEV, weight=weight, W=W, fake_quantizer=lc.FakeQuantizer)
+    a, b = ref.layers[0].proj.weight.data, ours.layers[0].proj.weight.data
+    assert a.dtype == b.dtype == torch.bfloat16
+    assert torch.equal(a.cpu(), b.cpu()), int((a.cpu() != b.cpu()).sum())
+    assert not hasattr(ours.layers[0].proj, "weight_quantizer")          # the driver deleted OUR module like its own
+
+
+@pytest.mark.parametrize("N,K,weight", [(1024, 2048, "int4-g[128]-rw"), (512, 1024, "nvfp4_e2m1-g[16]-rw"),
+                                          (256, 1024, "int4-g[-1]-zp-rw")])
+def test_reference_gptq_with_swapped_hook_solver_and_quantizer(N, K, weight):
+    import llm_compressor_b200 as lc
+    from llm_compressor_b200 import solvers
+    W = _w(N, K, 11)
+    n_samples, seq = 8, 512
+    ref, _, _ = ref_timing.run_gptq(N, K, n_samples, seq, DEV, weight=weight, W=W)
+
+    def patch(G):
+        G.update_weight = solvers.update_weight
+
+    ours, hook_s, upd_s = ref_timing.run_gptq(N, K, n_samples, seq, DEV, weight=weight, W=W, patch=patch,
+                                              fake_quantizer=lc.FakeQuantizer, hook_override=solvers.cache_hessian_weight)
+    assert len(hook_s) == n_samples                                       # OUR hook ran once per sample inside THEIR loop
+    a, b = ref.layers[0].proj.weight.data.float().cpu(), ours.layers[0].proj.weight.data.float().cpu()
+    same = float((a == b).float().mean())
+    X = ref.embed.weight.data.float().cpu()[:256]
+    W32 = W.float()
+
+    def sqnr(q):
+        r = X @ W32.T
+        return float(10 * torch.log10((r ** 2).sum() / ((r - X @ q.T) ** 2).sum()))
+
+    print(f"{weight} {N}x{K}: identical weights {same:.5f}, SQNR reference {sqnr(a):.3f} dB, swapped {sqnr(b):.3f} dB")
+    assert abs(sqnr(a) - sqnr(b)) < 0.1
+    assert same > 0.98          # both sides run fp32 Hessians / factors with different summation orders; see DESIGN.md section 2
+    assert not hasattr(ours.layers[0].proj, "weight_quantizer")

@@ -342,6 +342,45 @@ def test_gptq_headline_shapes_vs_oracle(N, K, gemm_mode):
     assert relf(got, ref) < 3e-2
 
 
+def test_shared_factor_with_mixed_precision_group(gemm_mode):
+    """Linears that share a Hessian may carry different quantizers (per-layer mixed precision: int4 q_proj,
+    int8 k_proj, int4 v_proj at the same group size, ref: utils/parser.py register_4_to_8bit_config).  The shared-factor
+    path must quantise every Linear with ITS quantizer: identical to solving them one by one."""
+    from llm_compressor_b200 import solvers
+    K, T = 1024, 2048
+    g = torch.Generator().manual_seed(5)
+    X = (torch.randn(T, K, generator=g) * torch.exp(0.8 * torch.randn(K, generator=g))).to(torch.bfloat16).to(DEV).float()
+    H = ((2.0 / T) * X.T @ X).contiguous()
+    fmts = [("int4", 384), ("int8", 128), ("int4", 256)]
+    Ws = [(0.02 * torch.randn(n, K, generator=g)).to(torch.bfloat16) for _, n in fmts]
+
+    def layers():
+        return [_layer(W, dict(type="int", format=f, group_size=128, axes=-1, zero_point=False, is_profile=False))
+                for (f, _), W in zip(fmts, Ws)]
+
+    one_by_one = layers()
+    for lin in one_by_one:
+        lin.weight_quantizer.H = H.clone()
+        solvers.update_weight(lin, DEV, actorder=True)
+    shared = layers()
+    fac = solvers.factorize(H.clone(), 128, actorder=True, percdamp=0.01)
+    by_q = {}
+    for lin in shared:
+        by_q.setdefault(solvers.quantizer_key(lin.weight_quantizer), []).append(lin)
+    assert len(by_q) == 2
+    for same in by_q.values():
+        solvers.update_weights_shared(same, DEV, fac)
+    solvers.update_weights_shared(layers(), DEV, fac)   # a mixed list must not be stacked either (falls back per layer)
+    for a, b, (f, _) in zip(one_by_one, shared, fmts):
+        same = float((a.weight.data == b.weight.data).float().mean())
+        nvals = int(torch.unique((a.weight.data.float() / a.weight.data.float().abs().amax(1, keepdim=True))).numel())
+        print(f"{f}: identical to the separate solve {same:.6f}, distinct normalised levels {nvals}")
+        assert same > (0.999 if gemm_mode.startswith("tcgen05") else 0.99999)   # tensor-core mode: run-to-run last-bit order
+    # the int8 Linear really was quantised with 8 bits (an int4 solve has at most 15 levels per group)
+    w8 = shared[1].weight.data.float()[:, :128]
+    assert int(torch.unique(w8[0]).numel()) > 16
+
+
 def test_sparsegpt_vs_oracle_seeded(gemm_mode):
     from llm_compressor_b200 import solvers
     N, K, T = 768, 1024, 1024
