@@ -1,80 +1,72 @@
-"""Fake-quant wrapper modules with the reference's interface.
+"""Fake-quant operator wrappers around the CUDA quantizers.
 
-ref: llm_compressor/modules/qlinear.py:16-88 (QLinear), llm_compressor/modules/qmatmul.py:16-65
-(QMatmul).  The wrappers stay PyTorch modules (north_star); their quantizers are the CUDA-backed
-ones of llm_compressor_b200.quantizers.
+The reference's wrappers (modules/qlinear.py, modules/qmatmul.py) are torch glue that stays the reference's own
+code in a drop-in deployment: `bind_reference()` points THEIR modules at this package's `FakeQuantizer` factory and
+nothing else changes (tests/test_reference_dropin_gpu.py runs the reference's QLinear that way).  For use without the
+reference tree, `QLinear` / `QMatmul` below offer the same constructor arguments and attribute names
+(`input_quantizer`, `weight_quantizer`, `output_quantizer`; `input1_quantizer`, `input2_quantizer`) on a small
+slot-table design; the SpinQuant-training online rotation kwargs of the reference's forward are out of scope here
+(offline rotation: llm_compressor_b200.hadamard.rotate_model).
 """
-from copy import deepcopy
-
 import torch
 import torch.nn.functional as F
-from torch import Tensor, nn
+from torch import nn
 
 from .quantizers import FakeQuantizer
 
 
-def _get(cfg, key):
-    return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
+def bind_reference(*reference_modules):
+    """Swap this package's quantizer factory into reference modules that did `from quantization.quant import
+    FakeQuantizer` (modules/qlinear.py:13, modules/qmatmul.py:13); returns the previous bindings for undoing."""
+    previous = [getattr(m, "FakeQuantizer", None) for m in reference_modules]
+    for m in reference_modules:
+        m.FakeQuantizer = FakeQuantizer
+    return previous
+
+
+def _cfg(quant_config, key):
+    return quant_config[key] if isinstance(quant_config, dict) else getattr(quant_config, key)
+
+
+def _slots(owner, quant_config, table, kwargs):
+    """table: {attribute name: (config key, op-name suffix, overrides or None)} -> quantizer sub-modules on `owner`."""
+    op, path = kwargs.get("op_name"), kwargs.get("save_path", "./")
+    for attr, (key, suffix, override) in table.items():
+        cfg = _cfg(quant_config, key)
+        if override:
+            cfg = dict(cfg, **override)
+        setattr(owner, attr, FakeQuantizer.build(cfg, op_name=f"{op}.{suffix}", save_path=path))
 
 
 class QLinear(nn.Linear):
-    def __init__(self, linear: nn.Linear, quant_config, dtype, **kwargs):
+    """y = Q_out(linear(Q_in(x), W, b)); `weight_quantizer` is applied by the calibration drivers, not in forward
+    (ref: modules/qlinear.py:86-88)."""
+
+    def __init__(self, linear, quant_config, dtype, **kwargs):
         super().__init__(linear.in_features, linear.out_features, linear.bias is not None, linear.weight.device, dtype)
-        op_name = kwargs.get("op_name", None)
-        save_path = kwargs.get("save_path", "./")
         self.train(linear.training)
-        with torch.no_grad():
-            self.weight.copy_(linear.weight)
-            if self.bias is not None:
-                self.bias.copy_(linear.bias)
-        self.input_quantizer = FakeQuantizer.build(_get(quant_config, "act_in"), op_name=f"{op_name}.input", save_path=save_path)
-        self.weight_quantizer = FakeQuantizer.build(_get(quant_config, "weight"), op_name=f"{op_name}.weight", save_path=save_path)
-        self.output_quantizer = FakeQuantizer.build(_get(quant_config, "act_out"), op_name=f"{op_name}.output", save_path=save_path)
+        self.load_state_dict({k: v.to(dtype) for k, v in linear.state_dict().items()})
+        _slots(self, quant_config, {"input_quantizer": ("act_in", "input", None), "weight_quantizer": ("weight", "weight", None),
+                                    "output_quantizer": ("act_out", "output", None)}, kwargs)
 
-    def forward(self, inputs: Tensor, **kwargs) -> Tensor:
-        R1 = kwargs.get("R1", None)
-        if R1 is not None:  # online rotation branch used by the SpinQuant training model (qlinear.py:59-84)
-            dtype = self.weight.dtype
-            transpose = kwargs.get("transpose", False)
-            if not transpose:
-                weight = self.weight.to(torch.float64) @ R1.to(torch.float64)
-            else:
-                weight = R1.T.to(torch.float64) @ self.weight.to(torch.float64)
-            R2 = kwargs.get("R2", None)
-            if R2 is not None:
-                had_dim = R2.shape[0]
-                if transpose:
-                    init_shape = weight.shape
-                    temp = weight.reshape(-1, init_shape[-1] // had_dim, had_dim)
-                    weight = (temp.to(torch.float64) @ R2.to(torch.float64)).reshape(init_shape)
-                else:
-                    W_ = weight.t()
-                    tshape = W_.shape
-                    temp = W_.reshape(-1, tshape[-1] // had_dim, had_dim)
-                    weight = (temp.to(torch.float64) @ R2.to(torch.float64)).reshape(tshape).t()
-            self.weight.data = self.weight_quantizer(weight.data.to(dtype))
+    def forward(self, inputs, **kwargs):
+        if kwargs.get("R1") is not None:
+            raise NotImplementedError("online R1 / R2 rotation belongs to the SpinQuant training model (out of scope); "
+                                      "rotate offline with llm_compressor_b200.hadamard.rotate_model")
         return self.output_quantizer(F.linear(self.input_quantizer(inputs), self.weight, self.bias))
-
-    def extra_repr(self):
-        return f"(in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None})"
 
 
 class QMatmul(nn.Module):
+    """Q_out(Q_1(a) @ Q_2(b)).  The second operand is grouped along `axes`: -1 for K^T in Q K^T (reduction dim last), -2 for
+    V in S V (groups run down the rows); a per-row / per-column group size follows the axis (ref: modules/qmatmul.py:34-46)."""
+
     def __init__(self, quant_config, axes=-1, **kwargs):
         super().__init__()
-        op_name = kwargs.get("op_name", None)
-        save_path = kwargs.get("save_path", "./")
-        act_in = dict(_get(quant_config, "act_in"))
-        act_in2 = deepcopy(act_in)
-        self.input1_quantizer = FakeQuantizer.build(act_in, op_name=f"{op_name}.input1", save_path=save_path)
-        act_in2["axes"] = axes
-        if (axes == -1) and (act_in.get("group_size") == -2):
-            act_in2["group_size"] = -1
-        if (axes == -2) and (act_in.get("group_size") == -1):
-            act_in2["group_size"] = -2
-        self.input2_quantizer = FakeQuantizer.build(act_in2, op_name=f"{op_name}.input2", save_path=save_path)
-        self.output_quantizer = FakeQuantizer.build(_get(quant_config, "act_out"), op_name=f"{op_name}.output", save_path=save_path)
+        gs = dict(_cfg(quant_config, "act_in")).get("group_size")
+        follow = {(-1, -2): -1, (-2, -1): -2}.get((axes, gs))
+        second = {"axes": axes} if follow is None else {"axes": axes, "group_size": follow}
+        _slots(self, quant_config, {"input1_quantizer": ("act_in", "input1", None), "input2_quantizer": ("act_in", "input2", second),
+                                    "output_quantizer": ("act_out", "output", None)}, kwargs)
 
-    def forward(self, inputs1: Tensor, inputs2: Tensor) -> Tensor:
-        return self.output_quantizer(
-            torch.matmul(self.input1_quantizer(inputs1).to(inputs2), self.input2_quantizer(inputs2)))
+    def forward(self, inputs1, inputs2):
+        return self.output_quantizer(torch.matmul(self.input1_quantizer(inputs1).to(inputs2), self.input2_quantizer(inputs2)))
