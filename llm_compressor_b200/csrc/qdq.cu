@@ -5,6 +5,7 @@
 //
 // Replaces ref: quantizers/{int,fp,mx,nvfp}_quant.py find_params/forward/fake_quantize and
 // quantizers/utils.py _reshape_to_blocks/_undo_reshape_to_blocks/_quantize_elemwise_core.
+#include <algorithm>
 #include <type_traits>
 
 #include "qdq_fast.cuh"
@@ -81,7 +82,8 @@ template <typename T, int LPG, bool NVFP_PASS1>
 __global__ void __launch_bounds__(256) qdq_subwarp_kernel(QdqArgs a, uint32_t* amax_key) {
   constexpr int DT = DtOf<T>::value;
   constexpr int VEC = 16 / sizeof(T);
-  constexpr int GPW = 32 / LPG;  // groups per warp
+  constexpr int GPW = 32 / LPG;  // groups per warp and step
+  constexpr int U = 4;           // steps in flight per warp: four 16-byte loads per lane before the first reduction
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPG, sl = lane % LPG;
   const int64_t total = a.nrows * a.G;
@@ -95,46 +97,52 @@ __global__ void __launch_bounds__(256) qdq_subwarp_kernel(QdqArgs a, uint32_t* a
   if (!NVFP_PASS1 && a.c.qtype == LCB_Q_NVFP && a.find) nv_g = *a.nv_amax;
   float local_amax = 0.0f;
 
-  for (int64_t g0 = warp * GPW; g0 < total; g0 += nwarps * GPW) {
-    const int64_t gid = g0 + sub;
-    const bool active = gid < total;
-    const int64_t r = active ? gid / a.G : 0;
-    const int64_t b = active ? gid - r * a.G : 0;
-    const int64_t col = b * a.group + (int64_t)sl * VEC;
-    const bool inb = active && col < a.cols;
-    float v[VEC];
+  for (int64_t g0 = warp * GPW * U; g0 < total; g0 += nwarps * GPW * U) {
+    float v[U][VEC];
+    int64_t gid[U], off[U];
+    bool active[U], inb[U];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) v[i] = 0.0f;
-    if (inb) load16<T>(x + r * a.cols + col, v);
-    float s, z;
-    if (a.find) {
-      float mx = -INFINITY, mn = INFINITY, amax = 0.0f;
-      stats_of<T, VEC>(v, mx, mn, amax);  // out-of-range lanes contribute the zero padding
+    for (int u = 0; u < U; ++u) {
+      gid[u] = g0 + u * GPW + sub;
+      active[u] = gid[u] < total;
+      const int64_t r = active[u] ? gid[u] / a.G : 0;
+      const int64_t b = active[u] ? gid[u] - r * a.G : 0;
+      const int64_t col = b * a.group + (int64_t)sl * VEC;
+      inb[u] = active[u] && col < a.cols;
+      off[u] = r * a.cols + col;
 #pragma unroll
-      for (int o = 1; o < LPG; o <<= 1) {
-        mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        amax = nan_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-      }
-      if constexpr (NVFP_PASS1) {
-        float vb, zb;
-        nvfp_block_stat<DT>(mx, mn, amax, a.c.zero_point, vb, zb);
-        if (active) local_amax = fmaxf(local_amax, fabsf(vb));
-        continue;
-      }
-      find_params<DT, DT>(a.c, mx, mn, amax, nv_g, s, z);
-      if (active && sl == 0) {
-        flag_nan_scale(a, s);
-        if (sc != nullptr) sc[gid] = from_f<T>(s);
-        if (zr != nullptr) zr[gid] = from_f<T>(z);
-      }
-    } else {
-      s = active ? to_f<T>(sc[gid]) : 1.0f;
-      z = active ? to_f<T>(zr[gid]) : 0.0f;
+      for (int i = 0; i < VEC; ++i) v[u][i] = 0.0f;
+      if (inb[u]) load16<T>(x + off[u], v[u]);
     }
-    if (a.apply && inb) {
-      const int64_t off = r * a.cols + col;
-      apply_vec<T, VEC>(a, v, s, z, out + off, a.codes ? a.codes + off : nullptr);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s, z;
+      if (a.find) {
+        float mx = -INFINITY, mn = INFINITY, amax = 0.0f;
+        stats_of<T, VEC>(v[u], mx, mn, amax);  // out-of-range lanes contribute the zero padding
+#pragma unroll
+        for (int o = 1; o < LPG; o <<= 1) {
+          mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          amax = nan_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        }
+        if constexpr (NVFP_PASS1) {
+          float vb, zb;
+          nvfp_block_stat<DT>(mx, mn, amax, a.c.zero_point, vb, zb);
+          if (active[u]) local_amax = fmaxf(local_amax, fabsf(vb));
+          continue;
+        }
+        find_params<DT, DT>(a.c, mx, mn, amax, nv_g, s, z);
+        if (active[u] && sl == 0) {
+          flag_nan_scale(a, s);
+          if (sc != nullptr) sc[gid[u]] = from_f<T>(s);
+          if (zr != nullptr) zr[gid[u]] = from_f<T>(z);
+        }
+      } else {
+        s = active[u] ? to_f<T>(sc[gid[u]]) : 1.0f;
+        z = active[u] ? to_f<T>(zr[gid[u]]) : 0.0f;
+      }
+      if (a.apply && inb[u]) apply_vec<T, VEC>(a, v[u], s, z, out + off[u], a.codes ? a.codes + off[u] : nullptr);
     }
   }
   if constexpr (NVFP_PASS1) {
@@ -712,6 +720,499 @@ __global__ void __launch_bounds__(256) tensor_apply_kernel(QdqArgs a, const uint
 }
 
 // ------------------------------------------------------------------------------------------
+// Bandwidth-shaped forms of the two-pass granularities (north_star: per-tensor and per-channel at the HBM roofline too).
+// Same op-by-op arithmetic as the generic kernels (qmath.cuh), different memory shape: FLAT launches -- a CTA takes a
+// fixed slab and retires, so CTAs in different phases share an SM and HBM always has requests in flight (the
+// grid-stride forms above measure 1.8 TB/s for per-tensor and 0.2 TB/s for axis -2 on a 403 MB tensor) -- and 128-bit
+// accesses on every path.
+//
+// per tensor, pass 1: min / max / amax of a slab of 4 x 256 vectors per CTA -> keys (as tensor_stats_kernel)
+template <typename T>
+__global__ void __launch_bounds__(256) tensor_stats_flat_kernel(const T* __restrict__ x, int64_t nvec, uint32_t* keys) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ float red[3][8];
+  float mx = -INFINITY, mn = INFINITY, amax = 0.0f;
+  const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  float v[4][VEC];
+  bool act[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = base + u * 256;
+    act[u] = i < nvec;
+    if (act[u]) load16<T>(x + i * VEC, v[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (act[u]) stats_of<T, VEC>(v[u], mx, mn, amax);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    amax = nan_max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = mx; red[1][wid] = mn; red[2][wid] = amax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      mx = nan_max(mx, red[0][k]); mn = nan_min(mn, red[1][k]); amax = nan_max(amax, red[2][k]);
+    }
+    atomicMax(&keys[0], f2key(mx));
+    atomicMax(&keys[1], f2key(-mn));
+    atomicMax(&keys[2], f2key(amax));
+  }
+}
+
+// per tensor, pass 2: 2 x 256 vectors per CTA
+template <typename T>
+__global__ void __launch_bounds__(256) tensor_apply_flat_kernel(QdqArgs a, const uint32_t* keys, int64_t nvec) {
+  constexpr int DT = DtOf<T>::value;
+  constexpr int VEC = 16 / sizeof(T);
+  const T* x = static_cast<const T*>(a.x);
+  T* out = static_cast<T*>(a.out);
+  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
+  float v[2][VEC];
+  bool act[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int64_t i = base + u * 256;
+    act[u] = i < nvec;
+    if (act[u]) load16<T>(x + i * VEC, v[u]);
+  }
+  float s, z;
+  if (a.find) {
+    const float mx = key2f(keys[0]), mn = -key2f(keys[1]), amax = key2f(keys[2]);
+    if (a.c.qtype == LCB_Q_INT) int_params<DT, LCB_F32>(mx, mn, amax, a.c.zero_point, a.c.f, s, z);
+    else fp_params<DT, LCB_F32>(mx, mn, amax, a.c.zero_point, a.c.f, s, z);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      flag_nan_scale(a, s);
+      if (a.scales) *static_cast<float*>(a.scales) = s;
+      if (a.zeros) *static_cast<float*>(a.zeros) = z;
+    }
+  } else {
+    s = *static_cast<const float*>(a.scales);
+    z = *static_cast<const float*>(a.zeros);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int64_t i = base + u * 256;
+    if (act[u]) apply_vec<T, VEC>(a, v[u], s, z, out + i * VEC, a.codes ? a.codes + i * VEC : nullptr);
+  }
+}
+
+// fp32 tensors, INT formats, groups along the last axis that tile the rows (the find_params / fake-quant of the permuted
+// fp32 weight inside GPTQ, ref: gptq/core.py:179,198,257): the generic sub-warp kernel spends ~65 instructions per
+// element (three NaN-propagating statistics, redundant parameters) and is issue bound at 2 TB/s.  Here a lane owns
+// 8 floats (32 bytes), LPG lanes a group; the statistics are plain fmax / fmin plus ONE integer maximum of the
+// magnitude bits that also detects non-finite inputs (those groups fall back to the NaN-propagating arithmetic);
+// apply is the IEEE op sequence of int_fq<fp32>.
+template <int LPG>
+__global__ void __launch_bounds__(256) qdq_stream_f32_kernel(QdqArgs a) {
+  const float* x = static_cast<const float*>(a.x);
+  float* out = static_cast<float*>(a.out);
+  float* sc = static_cast<float*>(a.scales);
+  float* zr = static_cast<float*>(a.zeros);
+  const bool zp = a.c.zero_point != 0;
+  const int64_t chunks = a.nrows * a.cols / 8;
+  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
+  float v[2][8];
+  int64_t c[2];
+  bool act[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    c[u] = base + u * 256;
+    act[u] = c[u] < chunks;
+    if (act[u]) {
+      const W8 w = ldg256(x + c[u] * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = __uint_as_float(w.w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = 0.0f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    float mx = v[u][0], mn = v[u][0];
+    uint32_t ab = __float_as_uint(v[u][0]) & 0x7fffffffu;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      if (zp) { mx = fmaxf(mx, v[u][i]); mn = fminf(mn, v[u][i]); }
+      ab = max(ab, __float_as_uint(v[u][i]) & 0x7fffffffu);
+    }
+#pragma unroll
+    for (int o = 1; o < LPG; o <<= 1) {
+      if (zp) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      ab = max(ab, __shfl_xor_sync(0xffffffffu, ab, o));
+    }
+    float s, z;
+    const bool finite = ab < 0x7f800000u;
+    if (finite) {
+      int_params<LCB_F32, LCB_F32>(mx, mn, __uint_as_float(ab), a.c.zero_point, a.c.f, s, z);
+    } else {  // NaN / inf somewhere in the group: torch.amax / amin propagate NaN
+      float gmx = -INFINITY, gmn = INFINITY, gam = 0.0f;
+      stats_of<float, 8>(v[u], gmx, gmn, gam);
+#pragma unroll
+      for (int o = 1; o < LPG; o <<= 1) {
+        gmx = nan_max(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+        gmn = nan_min(gmn, __shfl_xor_sync(0xffffffffu, gmn, o));
+        gam = nan_max(gam, __shfl_xor_sync(0xffffffffu, gam, o));
+      }
+      int_params<LCB_F32, LCB_F32>(gmx, gmn, gam, a.c.zero_point, a.c.f, s, z);
+    }
+    if (!act[u]) continue;
+    if ((c[u] & (LPG - 1)) == 0) {
+      flag_nan_scale(a, s);
+      const int64_t gid = c[u] / LPG;
+      if (sc != nullptr) sc[gid] = s;
+      if (zr != nullptr) zr[gid] = z;
+    }
+    if (!a.apply) continue;
+    W8 o;
+    const float qmax = a.c.f.qmax;
+    // all-equal asymmetric groups give s0 = 0 and a NaN / inf zero point (ref: int_quant.py:93-97): reference arithmetic
+    if (finite && s == s && (__float_as_uint(z) & 0x7f800000u) != 0x7f800000u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float q = __fadd_rn(__fdiv_rn(v[u][i], s), z);
+        q = fminf(fmaxf(rintf(q), -qmax), qmax);
+        o.w[i] = __float_as_uint(__fmul_rn(__fsub_rn(q, z), s));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float code;
+        o.w[i] = __float_as_uint(fake_quant<LCB_F32>(a.c, v[u][i], s, z, code));
+      }
+    }
+    stg256(out + c[u] * 8, o);
+  }
+}
+
+// per tensor, pass 1, bf16: packed NaN-propagating statistics (stats16), only the ones the parameters need --
+// (max, -min) for asymmetric, |x| maximum for symmetric; 4 x 256 chunks of 16 elements per CTA
+__global__ void __launch_bounds__(256) tensor_stats_stream_kernel(const __nv_bfloat16* __restrict__ x, int64_t chunks, int zp,
+                                                                  uint32_t* keys) {
+  __shared__ uint32_t red[8];
+  const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  W8 v[4];
+  bool act[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t c = base + u * 256;
+    act[u] = c < chunks;
+    v[u] = ldg256(x + (act[u] ? c : 0) * 16);     // idle slots re-read chunk 0: duplicates do not change max / min
+  }
+  Stat2 st = stats16(v[0], zp != 0);
+#pragma unroll
+  for (int u = 1; u < 4; ++u) {
+    const Stat2 t = stats16(v[u], zp != 0);
+    stat_combine(st, t, zp != 0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) stat_shfl_xor(st, o, zp != 0);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = zp ? st.mxmn : st.amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Stat2 t = st;
+    for (int k = 1; k < 8; ++k) {
+      Stat2 o;
+      o.mxmn = red[k]; o.amax = red[k];
+      stat_combine(t, o, zp != 0);
+    }
+    float mx, mn, amax;
+    stat_finish(t, zp != 0, mx, mn, amax);
+    if (zp) {
+      atomicMax(&keys[0], f2key(mx));
+      atomicMax(&keys[1], f2key(-mn));
+    } else {
+      atomicMax(&keys[2], f2key(amax));
+    }
+  }
+}
+
+// per tensor, pass 2, bf16 + INT formats: packed arithmetic (apply16_tensor), 2 x 256 chunks of 16 elements per CTA.
+// Non-finite parameters (NaN / inf in the tensor) and zero points that are not bf16-exact take the op-by-op arithmetic.
+template <int KIND>
+__global__ void __launch_bounds__(256) tensor_apply_stream_kernel(QdqArgs a, const uint32_t* keys, int64_t chunks) {
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a.x);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+  const int64_t base = (int64_t)blockIdx.x * 512 + threadIdx.x;
+  W8 v[2];
+  bool act[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int64_t c = base + u * 256;
+    act[u] = c < chunks;
+    if (act[u]) v[u] = ldg256(x + c * 16);
+  }
+  float s, z;
+  if (a.find) {
+    const float mx = key2f(keys[0]), mn = -key2f(keys[1]), amax = key2f(keys[2]);
+    int_params<LCB_BF16, LCB_F32>(mx, mn, amax, a.c.zero_point, a.c.f, s, z);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      flag_nan_scale(a, s);
+      if (a.scales) *static_cast<float*>(a.scales) = s;
+      if (a.zeros) *static_cast<float*>(a.zeros) = z;
+    }
+  } else {
+    s = *static_cast<const float*>(a.scales);
+    z = *static_cast<const float*>(a.zeros);
+  }
+  const bool fast = (__float_as_uint(s) & 0x7f800000u) != 0x7f800000u && (__float_as_uint(z) & 0x7f800000u) != 0x7f800000u &&
+                    z == R<LCB_BF16>(z) && fabsf(z) <= 256.0f;
+  const float rinv = __frcp_rn(s);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (!act[u]) continue;
+    if (fast) apply16_tensor<KIND>(v[u], s, rinv, z);
+    else v[u] = apply16_generic(a.c, v[u], s, z);
+    stg256(out + (base + u * 256) * 16, v[u]);
+  }
+}
+
+// axis -2, pass 1: a CTA reduces a [CG_ROWS rows x 32 * VEC columns] slab (a warp reads one 512-byte row segment per
+// step, 8 warps = 8 rows per step) and merges its column statistics into keys[(b, g, c)][3] with atomicMax; the slab
+// never crosses a group, so per-channel scaling of a tall tensor is spread over rows / CG_ROWS CTAs per column strip
+// instead of one (CG_ROWS: 128 for short groups, 1024 for tall ones -- fewer atomics per column).
+template <typename T>
+__global__ void __launch_bounds__(256) colgroup_stats_flat_kernel(QdqArgs a, uint32_t* keys, int64_t slabs_per_group, int CG_ROWS) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ float red[3][8][32 * VEC];
+  const T* x = static_cast<const T*>(a.x);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t bidx = blockIdx.z;
+  const int64_t g = blockIdx.y / slabs_per_group, slab = blockIdx.y % slabs_per_group;
+  const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * VEC;
+  const int64_t r0 = g * a.group + slab * CG_ROWS;
+  const int64_t r1 = min(min(r0 + CG_ROWS, (g + 1) * a.group), a.rows);
+  float mx[VEC], mn[VEC], am[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { mx[j] = -INFINITY; mn[j] = INFINITY; am[j] = 0.0f; }
+  const T* xb = x + bidx * a.rows * a.cols;
+  if (c0 < a.cols) {
+#pragma unroll 4
+    for (int64_t r = r0 + wid; r < r1; r += 8) {
+      float v[VEC];
+      load16<T>(xb + r * a.cols + c0, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        mx[j] = nan_max(mx[j], v[j]); mn[j] = nan_min(mn[j], v[j]); am[j] = nan_max(am[j], fabsf(v[j]));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    red[0][wid][lane * VEC + j] = mx[j]; red[1][wid][lane * VEC + j] = mn[j]; red[2][wid][lane * VEC + j] = am[j];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 32 * VEC; t += 256) {
+    const int64_t cc = (int64_t)blockIdx.x * 32 * VEC + t;
+    if (cc >= a.cols) continue;
+    float fmx = -INFINITY, fmn = INFINITY, fam = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      fmx = nan_max(fmx, red[0][k][t]); fmn = nan_min(fmn, red[1][k][t]); fam = nan_max(fam, red[2][k][t]);
+    }
+    // a group cut short by the end of the tensor is zero padded (ref: utils.py:119-132); only its last slab knows
+    if (r1 == a.rows && a.rows < (g + 1) * a.group) { fmx = nan_max(fmx, 0.0f); fmn = nan_min(fmn, 0.0f); }
+    uint32_t* kp = keys + ((bidx * a.G + g) * a.cols + cc) * 3;
+    atomicMax(kp + 0, f2key(fmx));
+    atomicMax(kp + 1, f2key(-fmn));
+    atomicMax(kp + 2, f2key(fam));
+  }
+}
+
+// axis -2, pass 1, bf16: the same slab decomposition with packed bf16x2 statistics -- a lane's 8 columns are four
+// packed registers and the reduction DOWN the rows is an elementwise __hmax2_nan / __hmin2_nan per register (one
+// instruction per two elements), only the statistics the parameters need.
+__global__ void __launch_bounds__(256) colgroup_stats_stream_kernel(QdqArgs a, uint32_t* keys, int64_t slabs_per_group,
+                                                                    int CG_ROWS) {
+  __shared__ uint32_t red[2][8][32 * 4];
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a.x);
+  const bool zp = a.c.zero_point != 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t bidx = blockIdx.z;
+  const int64_t g = blockIdx.y / slabs_per_group, slab = blockIdx.y % slabs_per_group;
+  const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * 8;
+  const int64_t r0 = g * a.group + slab * CG_ROWS;
+  const int64_t r1 = min(min(r0 + (int64_t)CG_ROWS, (g + 1) * a.group), a.rows);
+  const uint32_t NINF2 = 0xff80ff80u, PINF2 = 0x7f807f80u;
+  uint32_t mx[4], mn[4];   // symmetric: mx holds the |x| maxima
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { mx[j] = zp ? NINF2 : 0u; mn[j] = PINF2; }
+  const __nv_bfloat16* xb = x + bidx * a.rows * a.cols;
+  if (c0 < a.cols) {
+#pragma unroll 4
+    for (int64_t r = r0 + wid; r < r1; r += 8) {
+      const uint4 t = *reinterpret_cast<const uint4*>(xb + r * a.cols + c0);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (zp) {
+          mx[j] = bf22u(__hmax2_nan(u2bf2(mx[j]), u2bf2(w[j])));
+          mn[j] = bf22u(__hmin2_nan(u2bf2(mn[j]), u2bf2(w[j])));
+        } else {
+          mx[j] = bf22u(__hmax2_nan(u2bf2(mx[j]), u2bf2(w[j] & 0x7fff7fffu)));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[0][wid][lane * 4 + j] = mx[j]; red[1][wid][lane * 4 + j] = mn[j]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int t = threadIdx.x;                      // packed register t covers columns 2t, 2t+1 of the strip
+    uint32_t fx = red[0][0][t], fn = red[1][0][t];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      fx = bf22u(__hmax2_nan(u2bf2(fx), u2bf2(red[0][k][t])));
+      if (zp) fn = bf22u(__hmin2_nan(u2bf2(fn), u2bf2(red[1][k][t])));
+    }
+    const bool pad = r1 == a.rows && a.rows < (g + 1) * a.group;   // zero padded tail group (ref: utils.py:119-132)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t cc = (int64_t)blockIdx.x * 256 + 2 * t + h;
+      if (cc >= a.cols) continue;
+      float vx = __uint_as_float(h ? (fx & 0xffff0000u) : (fx << 16));
+      float vn = __uint_as_float(h ? (fn & 0xffff0000u) : (fn << 16));
+      uint32_t* kp = keys + ((bidx * a.G + g) * a.cols + cc) * 3;
+      if (zp) {
+        if (pad) { vx = nan_max(vx, 0.0f); vn = nan_min(vn, 0.0f); }
+        atomicMax(kp + 0, f2key(vx));
+        atomicMax(kp + 1, f2key(-vn));
+      } else {
+        atomicMax(kp + 2, f2key(vx));
+      }
+    }
+  }
+}
+
+// axis -2: keys -> parameters (NVFP: the block statistic, finalised by colgroup_nvfp_finalize_kernel)
+template <typename T>
+__global__ void __launch_bounds__(256) colgroup_params_kernel(QdqArgs a, const uint32_t* keys, T* sc, T* zr, int64_t n,
+                                                              uint32_t* amax_key) {
+  constexpr int DT = DtOf<T>::value;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float fmx = key2f(keys[3 * i]), fmn = -key2f(keys[3 * i + 1]), fam = key2f(keys[3 * i + 2]);
+  // the packed bf16 statistics pass leaves the ones the configuration does not use unset (key 0)
+  if (keys[3 * i + 2] == 0u) fam = nan_max(fabsf(fmx), fabsf(fmn));
+  if (keys[3 * i] == 0u) { fmx = fam; fmn = -fam; }
+  float s, z;
+  if (a.c.qtype == LCB_Q_NVFP) {
+    nvfp_block_stat<DT>(fmx, fmn, fam, a.c.zero_point, s, z);
+    atomicMax(amax_key, __float_as_uint(fabsf(s)));
+  } else {
+    find_params<DT, DT>(a.c, fmx, fmn, fam, 0.0f, s, z);
+    flag_nan_scale(a, s);
+  }
+  sc[i] = from_f<T>(s);
+  zr[i] = from_f<T>(z);
+}
+
+// axis -2, pass 2: a thread quantises one 16-byte vector with the 16-byte vectors of its columns' parameters
+template <typename T>
+__global__ void __launch_bounds__(256) colgroup_apply_flat_kernel(QdqArgs a, const T* __restrict__ sc, const T* __restrict__ zr) {
+  constexpr int DT = DtOf<T>::value;
+  constexpr int VEC = 16 / sizeof(T);
+  const T* x = static_cast<const T*>(a.x);
+  T* out = static_cast<T*>(a.out);
+  const int64_t vpr = a.cols / VEC;                       // vectors per row
+  const int64_t nvec = a.nrows * a.rows * vpr;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int64_t i = (int64_t)blockIdx.x * 512 + u * 256 + threadIdx.x;
+    if (i >= nvec) continue;
+    const int64_t br = i / vpr, cv = i - br * vpr;
+    const int64_t r = br % a.rows, b = br / a.rows;
+    const int64_t pidx = (b * a.G + r / a.group) * a.cols + cv * VEC;
+    float v[VEC], sv[VEC], zv[VEC], o[VEC];
+    load16<T>(x + i * VEC, v);
+    load16<T>(sc + pidx, sv);
+    load16<T>(zr + pidx, zv);
+    uint8_t cd[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float code;
+      o[j] = fake_quant<DT>(a.c, v[j], sv[j], zv[j], code);
+      cd[j] = encode_code(a.c, code);
+    }
+    store16<T>(out + i * VEC, o);
+    if (a.codes) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a.codes[i * VEC + j] = cd[j];
+    }
+  }
+}
+
+// axis -2, pass 2, bf16 + INT formats: a lane owns 16 columns (their 16 scales / zero points stay in registers as packed
+// bf16x2 pairs, loaded once) and walks down CA_ROWS / 8 rows of a [CA_ROWS x 512] tile; the per-column parameters are
+// bf16 (x.dtype), so the packed arithmetic of apply16 applies with (s_c, s_c+1) pairs.  Tiles never straddle a group.
+constexpr int CA_ROWS = 64;
+template <int KIND>
+__global__ void __launch_bounds__(256) colgroup_apply_stream_kernel(QdqArgs a, const __nv_bfloat16* __restrict__ sc,
+                                                                    const __nv_bfloat16* __restrict__ zr) {
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a.x);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * 16;
+  if (c0 >= a.cols) return;
+  const int64_t tiles_per_batch = a.rows / CA_ROWS;
+  const int64_t b = blockIdx.y / tiles_per_batch, r0 = (blockIdx.y % tiles_per_batch) * CA_ROWS;
+  const int64_t pidx = (b * a.G + r0 / a.group) * a.cols + c0;
+  const W8 sv = ldg256(sc + pidx), zv = ldg256(zr + pidx);
+  float rc[16];
+  bool finite = true;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t sw = sv.w[j], zw = zv.w[j];
+    finite = finite && ((sw & 0x7f80u) != 0x7f80u) && ((sw & 0x7f800000u) != 0x7f800000u) && ((zw & 0x7f80u) != 0x7f80u) &&
+             ((zw & 0x7f800000u) != 0x7f800000u);
+    rc[2 * j] = rcp_fast(__uint_as_float(sw << 16));
+    rc[2 * j + 1] = rcp_fast(__uint_as_float(sw & 0xffff0000u));
+  }
+  const __nv_bfloat16* xb = x + (b * a.rows + r0) * a.cols + c0;
+  __nv_bfloat16* ob = out + (b * a.rows + r0) * a.cols + c0;
+#pragma unroll 2
+  for (int r = wid; r < CA_ROWS; r += 8) {
+    W8 v = ldg256(xb + (int64_t)r * a.cols);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t w = v.w[j], sw = sv.w[j], zw = zv.w[j];
+      const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+      if (finite) {
+        __nv_bfloat162 q = u2bf2(pack_bf2(mul_snap(x0, rc[2 * j]), mul_snap(x1, rc[2 * j + 1])));
+        const __nv_bfloat162 z2 = u2bf2(zw), s2 = u2bf2(sw);
+        q = __hadd2_rn(q, z2);
+        if constexpr (KIND == FK_INT4) {
+          q = __hmin2(__hmax2(q, u2bf2(0xc0e0c0e0u)), u2bf2(0x40e040e0u));
+          const __nv_bfloat162 magic = u2bf2(0x43404340u);
+          q = __hsub2_rn(__hadd2_rn(q, magic), magic);
+        } else {
+          q = __hmin2(__hmax2(q, u2bf2(0xc2fec2feu)), u2bf2(0x42fe42feu));
+          const uint32_t qb = bf22u(q);
+          const float MG = 12582912.0f;
+          q = u2bf2(pack_bf2(__fsub_rn(__fadd_rn(__uint_as_float(qb << 16), MG), MG),
+                             __fsub_rn(__fadd_rn(__uint_as_float(qb & 0xffff0000u), MG), MG)));
+        }
+        v.w[j] = bf22u(__hmul2_rn(__hsub2_rn(q, z2), s2));
+      } else {   // a non-finite parameter among my 16 columns: op-by-op reference arithmetic for all of them
+        float code;
+        const float o0 = fake_quant<LCB_BF16>(a.c, x0, __uint_as_float(sw << 16), __uint_as_float(zw << 16), code);
+        const float o1 = fake_quant<LCB_BF16>(a.c, x1, __uint_as_float(sw & 0xffff0000u), __uint_as_float(zw & 0xffff0000u), code);
+        v.w[j] = (__float_as_uint(o0) >> 16) | (__float_as_uint(o1) & 0xffff0000u);
+      }
+    }
+    stg256(ob + (int64_t)r * a.cols, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host dispatch
 static int grid_for(int64_t work_items, int64_t items_per_cta, int ctas_per_sm) {
   int64_t need = ceil_div(work_items, items_per_cta);
@@ -879,9 +1380,28 @@ static int launch_rowwise(const QdqArgs& a, uint32_t* amax_key, cudaStream_t st)
       if (a.group <= (int64_t)256 * VEC * 8) return launch_rowcta_fast(a, kind, total, st);
     }
   }
+  if constexpr (std::is_same<T, float>::value && !P1) {
+    const int64_t l8 = a.group / 8;
+    if (a.c.qtype == LCB_Q_INT && a.find && !a.mse && a.codes == nullptr && a.group % 8 == 0 && a.cols == a.G * a.group &&
+        l8 >= 1 && l8 <= 32 && (l8 & (l8 - 1)) == 0 &&
+        ((reinterpret_cast<uintptr_t>(a.x) | (a.apply ? reinterpret_cast<uintptr_t>(a.out) : 0)) & 31) == 0) {
+      const unsigned grid = (unsigned)ceil_div(a.nrows * a.cols / 8, 512);
+      switch (l8) {
+        case 1: qdq_stream_f32_kernel<1><<<grid, 256, 0, st>>>(a); break;
+        case 2: qdq_stream_f32_kernel<2><<<grid, 256, 0, st>>>(a); break;
+        case 4: qdq_stream_f32_kernel<4><<<grid, 256, 0, st>>>(a); break;
+        case 8: qdq_stream_f32_kernel<8><<<grid, 256, 0, st>>>(a); break;
+        case 16: qdq_stream_f32_kernel<16><<<grid, 256, 0, st>>>(a); break;
+        default: qdq_stream_f32_kernel<32><<<grid, 256, 0, st>>>(a); break;
+      }
+      LCB_LAUNCH_CHECK();
+      return LCB_OK;
+    }
+  }
   if (vec_ok && lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0) {
     const int gpw = 32 / (int)lpg;
-    const int grid = grid_for(total, (int64_t)8 * gpw, 8);
+    // flat: every warp takes one set of groups and the CTA retires (see qdq_stream.cuh on grid-stride vs flat)
+    const int grid = (int)std::min<int64_t>(ceil_div(total, (int64_t)8 * gpw * 4), (int64_t)1 << 30);
     switch (lpg) {
       case 1: qdq_subwarp_kernel<T, 1, P1><<<grid, 256, 0, st>>>(a, amax_key); break;
       case 2: qdq_subwarp_kernel<T, 2, P1><<<grid, 256, 0, st>>>(a, amax_key); break;
@@ -911,12 +1431,41 @@ static int qdq_typed(QdqArgs a, int axis, int64_t batch, void* ws, size_t ws_byt
   const bool nvfp = a.c.qtype == LCB_Q_NVFP;
   if (a.group == 0) {  // per tensor
     const int64_t n = a.nrows * a.cols;
+    constexpr int VEC = 16 / sizeof(T);
+    const bool flat = n % VEC == 0 && n >= 4096 &&
+                      ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out) |
+                        (a.codes ? reinterpret_cast<uintptr_t>(a.codes) : 0)) & 15) == 0;
     if (a.find) {
       LCB_CUDA(cudaMemsetAsync(keys, 0, 16, st));
-      tensor_stats_kernel<T><<<grid_for(n, 256 * 16, 4), 256, 0, st>>>(static_cast<const T*>(a.x), n, keys);
+      bool packed = false;
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        if (flat && n % 16 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 31) == 0) {
+          tensor_stats_stream_kernel<<<(unsigned)ceil_div(n / 16, 1024), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a.x), n / 16,
+                                                                                  a.c.zero_point, keys);
+          packed = true;
+        }
+      }
+      if (packed) {
+      } else if (flat) tensor_stats_flat_kernel<T><<<(unsigned)ceil_div(n / VEC, 1024), 256, 0, st>>>(static_cast<const T*>(a.x), n / VEC, keys);
+      else tensor_stats_kernel<T><<<grid_for(n, 256 * 16, 4), 256, 0, st>>>(static_cast<const T*>(a.x), n, keys);
       LCB_LAUNCH_CHECK();
     }
-    if (a.apply || a.scales || a.zeros) {
+    bool done = false;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      if (a.apply && flat && a.c.qtype == LCB_Q_INT && a.codes == nullptr && n % 16 == 0 &&
+          ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 31) == 0) {
+        const unsigned g = (unsigned)ceil_div(n / 16, 512);
+        if (a.c.f.mbits == 4) tensor_apply_stream_kernel<FK_INT4><<<g, 256, 0, st>>>(a, keys, n / 16);
+        else tensor_apply_stream_kernel<FK_INT8><<<g, 256, 0, st>>>(a, keys, n / 16);
+        LCB_LAUNCH_CHECK();
+        done = true;
+      }
+    }
+    if (done) {
+    } else if (a.apply && flat) {
+      tensor_apply_flat_kernel<T><<<(unsigned)ceil_div(n / VEC, 512), 256, 0, st>>>(a, keys, n / VEC);
+      LCB_LAUNCH_CHECK();
+    } else if (a.apply || a.scales || a.zeros) {
       tensor_apply_kernel<T><<<a.apply ? grid_for(n, 256 * 16, 8) : 1, 256, 0, st>>>(a, keys, n);
       LCB_LAUNCH_CHECK();
     }
@@ -948,9 +1497,31 @@ static int qdq_typed(QdqArgs a, int axis, int64_t batch, void* ws, size_t ws_byt
     if (sc == nullptr) { sc = reinterpret_cast<T*>(p); p += (size_t)nparams * sizeof(T); }
     if (zr == nullptr) { zr = reinterpret_cast<T*>(p); }
     if (nvfp && a.nv_amax == nullptr) LCB_CUDA(cudaMemsetAsync(keys, 0, 16, st));
-    dim3 grid((unsigned)ceil_div(a.cols, 64), (unsigned)a.G, (unsigned)batch), block(32, 8);
-    colgroup_stats_kernel<T><<<grid, block, 0, st>>>(a, sc, zr, keys);
-    LCB_LAUNCH_CHECK();
+    constexpr int VEC = 16 / sizeof(T);
+    const size_t koff = (16 + 2 * (size_t)nparams * sizeof(T) + 15) & ~(size_t)15;
+    const int cg_rows = std::min<int64_t>(a.group, a.rows) <= 2048 ? 128 : 1024;
+    const int64_t spg = ceil_div(std::min<int64_t>(a.group, a.rows), cg_rows);   // row slabs per group
+    const bool flat_ok = a.cols % VEC == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
+                         ws_bytes >= koff + (size_t)nparams * 12 && a.G * spg <= 65535 && batch <= 65535;
+    if (flat_ok) {
+      // statistics as order-preserving keys [nparams][3] behind the parameter scratch, merged over row slabs
+      uint32_t* ckeys = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + koff);
+      LCB_CUDA(cudaMemsetAsync(ckeys, 0, (size_t)nparams * 12, st));
+      dim3 grid((unsigned)ceil_div(a.cols, 32 * VEC), (unsigned)(a.G * spg), (unsigned)batch);
+      bool packed = false;
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        colgroup_stats_stream_kernel<<<grid, 256, 0, st>>>(a, ckeys, spg, cg_rows);
+        packed = true;
+      }
+      if (!packed) colgroup_stats_flat_kernel<T><<<grid, 256, 0, st>>>(a, ckeys, spg, cg_rows);
+      LCB_LAUNCH_CHECK();
+      colgroup_params_kernel<T><<<(unsigned)ceil_div(nparams, 256), 256, 0, st>>>(a, ckeys, sc, zr, nparams, keys);
+      LCB_LAUNCH_CHECK();
+    } else {
+      dim3 grid((unsigned)ceil_div(a.cols, 64), (unsigned)a.G, (unsigned)batch), block(32, 8);
+      colgroup_stats_kernel<T><<<grid, block, 0, st>>>(a, sc, zr, keys);
+      LCB_LAUNCH_CHECK();
+    }
     if (nvfp) {
       const float* g = a.nv_amax ? a.nv_amax : reinterpret_cast<const float*>(keys);
       colgroup_nvfp_finalize_kernel<T><<<grid_for(nparams, 256, 4), 256, 0, st>>>(a, sc, nparams, g);
@@ -958,7 +1529,28 @@ static int qdq_typed(QdqArgs a, int axis, int64_t batch, void* ws, size_t ws_byt
     }
   }
   if (a.apply) {
-    colgroup_apply_kernel<T><<<grid_for(a.nrows * a.rows * a.cols, 256 * 8, 8), 256, 0, st>>>(a, sc, zr);
+    constexpr int VEC2 = 16 / sizeof(T);
+    const bool vec = a.cols % VEC2 == 0 && ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out) |
+                                              reinterpret_cast<uintptr_t>(sc) | reinterpret_cast<uintptr_t>(zr)) & 15) == 0;
+    bool done = false;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      if (a.c.qtype == LCB_Q_INT && a.codes == nullptr && a.cols % 16 == 0 && a.rows % CA_ROWS == 0 && a.group % CA_ROWS == 0 &&
+          a.nrows * (a.rows / CA_ROWS) <= 65535 &&
+          ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(sc) |
+            reinterpret_cast<uintptr_t>(zr)) & 31) == 0) {
+        dim3 g((unsigned)ceil_div(a.cols, 512), (unsigned)(a.nrows * (a.rows / CA_ROWS)));
+        if (a.c.f.mbits == 4) colgroup_apply_stream_kernel<FK_INT4><<<g, 256, 0, st>>>(a, sc, zr);
+        else colgroup_apply_stream_kernel<FK_INT8><<<g, 256, 0, st>>>(a, sc, zr);
+        done = true;
+      }
+    }
+    if (done) {
+    } else if (vec) {
+      const int64_t nvec = a.nrows * a.rows * (a.cols / VEC2);
+      colgroup_apply_flat_kernel<T><<<(unsigned)ceil_div(nvec, 512), 256, 0, st>>>(a, sc, zr);
+    } else {
+      colgroup_apply_kernel<T><<<grid_for(a.nrows * a.rows * a.cols, 256 * 8, 8), 256, 0, st>>>(a, sc, zr);
+    }
     LCB_LAUNCH_CHECK();
   }
   return LCB_OK;
@@ -995,7 +1587,8 @@ extern "C" size_t lcb_qdq_ws_bytes(const lcb_quant_cfg* cfg, int dtype, int64_t 
   size_t bytes = 16;
   if (group > 0 && axis == -2) {
     const size_t es = dtype == LCB_BF16 ? 2 : 4;
-    bytes += 2 * (size_t)(batch * ceil_div(rows, group) * cols) * es + 32;
+    const size_t np = (size_t)(batch * ceil_div(rows, group) * cols);
+    bytes += 2 * np * es + 32 + np * 12;   // parameter scratch + per-column statistic keys
   }
   return bytes;
 }

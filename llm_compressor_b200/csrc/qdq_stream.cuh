@@ -124,6 +124,45 @@ __device__ __forceinline__ void apply16(W8& v, float s, float z, bool zp) {
   }
 }
 
+// Per-tensor INT scaling: the scale is a 0-dim fp32 tensor in the reference (int_quant.py:93-102 on a 0-dim amax), so
+// x / s is RNE_bf16(RN_fp32(float(x) / s_fp32)) with an arbitrary 24-bit divisor: the exact-tie argument of div_snap does
+// not hold.  q0 = x * (1/s) is within 2 ulp of the quotient; whenever q0 lies within 16 ulp of a bf16 rounding tie the
+// true IEEE quotient is recomputed (about one element in 2^11), everything else cannot round differently.  The zero
+// point is an integer of magnitude <= 254 (exact in bf16), so + z / - z are the packed bf16 ops of apply16; only the
+// final * s goes through fp32 again.  All operands finite (the caller falls back to the generic kernel otherwise).
+template <int KIND>
+__device__ __forceinline__ void apply16_tensor(W8& v, float s, float rinv, float z) {
+  static_assert(KIND == FK_INT4 || KIND == FK_INT8, "per-tensor fast path: INT formats");
+  const __nv_bfloat162 z2 = u2bf2(dup_bf(z));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t w = v.w[i];
+    const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+    float q0 = __fmul_rn(x0, rinv), q1 = __fmul_rn(x1, rinv);
+    if (((__float_as_uint(q0) & 0xffffu) - 0x7ff0u) < 0x20u) q0 = __fdiv_rn(x0, s);
+    if (((__float_as_uint(q1) & 0xffffu) - 0x7ff0u) < 0x20u) q1 = __fdiv_rn(x1, s);
+    __nv_bfloat162 q = u2bf2(pack_bf2(q0, q1));
+    q = __hadd2_rn(q, z2);
+    float d0, d1;
+    if constexpr (KIND == FK_INT4) {
+      q = __hmin2(__hmax2(q, u2bf2(0xc0e0c0e0u)), u2bf2(0x40e040e0u));
+      const __nv_bfloat162 magic = u2bf2(0x43404340u);
+      q = __hsub2_rn(__hsub2_rn(__hadd2_rn(q, magic), magic), z2);
+      const uint32_t qb = bf22u(q);
+      d0 = __uint_as_float(qb << 16); d1 = __uint_as_float(qb & 0xffff0000u);
+    } else {
+      q = __hmin2(__hmax2(q, u2bf2(0xc2fec2feu)), u2bf2(0x42fe42feu));
+      const uint32_t qb = bf22u(q);
+      const float MG = 12582912.0f;
+      const float r0 = __fsub_rn(__fadd_rn(__uint_as_float(qb << 16), MG), MG);
+      const float r1 = __fsub_rn(__fadd_rn(__uint_as_float(qb & 0xffff0000u), MG), MG);
+      const uint32_t db = bf22u(__hsub2_rn(u2bf2(pack_bf2(r0, r1)), z2));
+      d0 = __uint_as_float(db << 16); d1 = __uint_as_float(db & 0xffff0000u);
+    }
+    v.w[i] = pack_bf2(__fmul_rn(d0, s), __fmul_rn(d1, s));
+  }
+}
+
 // op-by-op reference arithmetic for a chunk whose group parameters are not finite
 // (by value on purpose: a reference would force the caller's registers / kernel parameters into local memory)
 __device__ __noinline__ W8 apply16_generic(QCfg c, W8 v, float s, float z) {
