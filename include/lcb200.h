@@ -12,8 +12,14 @@
  *   - plain C: pointers + sizes only, no torch / CUDA types in the signatures.  `stream` is a
  *     cudaStream_t passed as void* (NULL = legacy default stream).
  *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`.
- *   - no hidden allocation: scratch memory is passed in (`ws`, `ws_bytes`); each call has a
- *     `*_ws_bytes` query.  Calls are asynchronous on `stream` and re-entrant.
+ *   - no hidden device allocation: scratch memory is passed in (`ws`, `ws_bytes`); each call has a
+ *     `*_ws_bytes` query.  Calls are asynchronous on `stream`.  Two pieces of library state exist and are
+ *     the only exceptions to re-entrancy: (1) lcb_set_gemm_mode() is a PROCESS-GLOBAL switch read by the
+ *     solver entry points (set it before concurrent use, not during); (2) the look-ahead schedules of
+ *     lcb_gptq_update / lcb_sparsegpt_update / lcb_gptaq_p and of the exact-mode lcb_chol_inv_upper use three
+ *     library-owned non-blocking side streams + events, created once per host thread and device and joined
+ *     back into `stream` before the call returns -- concurrent calls must come from different host threads
+ *     (or be serialised on one), each with its own workspace.
  *   - return value: LCB_OK or a negative LCB_ERR_*; lcb_last_error() gives a thread-local
  *     message.  Numerical trouble found on the device (NaN scales, non-SPD Hessian) is reported
  *     through the optional device word `status` (bit mask LCB_ST_*), which the caller reads
@@ -286,6 +292,26 @@ int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype_out, int64
  * lcb_unpack4 restores the uint8 codes (is_signed: sign-extend INT4 two's complement, else zero-extend fp4). */
 int lcb_pack4(const uint8_t* codes, uint8_t* packed, int64_t numel, void* stream);
 int lcb_unpack4(const uint8_t* packed, uint8_t* codes, int64_t numel, int is_signed, void* stream);
+
+/* ---- fused activation fake-quant + GEMM of the calibration forwards (ref: modules/qlinear.py:86-88
+ * `F.linear(input_quantizer(x), W, b)`):  y[m, n] = QDQ(x)[m, k] @ w[n, k]^T (+ bias), all bf16, fp32 accumulation on
+ * tcgen05.  cfg != NULL: INT4 / INT8 activation quantiser (symmetric or asymmetric) whose scales / zeros [m, k / group]
+ * (bf16, from lcb_qdq in FIND mode; group = k for per-token, else a multiple of 64 dividing k) are applied to each
+ * activation tile in shared memory in the GEMM's operand prologue -- the quantised activation never goes to HBM and is
+ * bit-identical to lcb_qdq's output.  cfg == NULL: plain bf16 GEMM.  Results equal F.linear's up to the fp32
+ * accumulation order (outputs differ by at most one bf16 ulp). */
+int lcb_qlinear_fwd(const lcb_quant_cfg* cfg, const void* x, const void* w, const void* bias, void* y, int64_t m, int64_t n,
+                    int64_t k, int64_t group, const void* scales, const void* zeros, void* stream);
+
+/* ---- numerical profile of a fake-quant op on the device (ref: quantizers/base.py:30-113 record_stats, which copies
+ * both tensors to the CPU and sorts one).  lcb_profile_stats writes 8 floats to `stats`: min / max of x, min / max of
+ * QDQ(x), and the sum over elements of ((x - min x) / (max x - min x) - (q - min q) / (max q - min q))^2 -- the
+ * ingredients of the reference's Max, QDQ(Max), ClipError and SQNR columns.  The PC99% column is an exact order
+ * statistic: lcb_profile_to_f32 + the lcb_select_* phases. */
+size_t lcb_profile_ws_bytes(void);
+int lcb_profile_stats(const void* x, const void* q, int dtype, int64_t n, float* stats, void* ws, size_t ws_bytes,
+                      void* stream);
+int lcb_profile_to_f32(const void* x, int dtype, float* out, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -127,6 +127,10 @@ _OPTIONAL = [
     ("lcb_rownorm_accum", [_vp, _vp, _i64, _i64, _f32, _f32, _vp], _i32),
     ("lcb_chol_ws_bytes", [_i64], _sz),
     ("lcb_chol_trace_offset", [_i64], _sz),
+    ("lcb_qlinear_fwd", [_cfgp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp], _i32),
+    ("lcb_profile_ws_bytes", [], _sz),
+    ("lcb_profile_stats", [_vp, _vp, _i32, _i64, _vp, _vp, _sz, _vp], _i32),
+    ("lcb_profile_to_f32", [_vp, _i32, _vp, _i64, _vp], _i32),
     ("lcb_hessian_dead_fix", [_vp, _i64, _vp, _vp], _i32),
     ("lcb_chol_inv_upper", [_vp, _vp, _i64, _vp, _f32, _vp, _sz, _vp, _vp], _i32),
     ("lcb_gptq_ws_bytes", [_i64, _i64, _i32], _sz),

@@ -19,7 +19,7 @@ import functools
 import torch
 from torch import nn
 
-from . import ops, solvers
+from . import parallel, ops, solvers
 
 
 def synthetic_loader(vocab_size, nsamples=128, seqlen=2048, seed=0):
@@ -146,12 +146,20 @@ def _quantize_head(model, device, mse):
 
 
 @torch.no_grad()
-def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, dataloader=None):
+def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, dataloader=None, distributed=False):
+    """ref: quantization/calibrations/gptq/core.py:21-160.
+    distributed=True under torch.distributed (one process per GPU): every rank runs the calibration
+    forwards of ITS samples only (parallel.sample_shard), the raw Hessian sums are all-reduced, every rank factors the
+    Hessian, solves its slice of the output rows and the slices are all-gathered -- all ranks end with the same model."""
+    dist_on = bool(distributed) and parallel.world()[1] > 1
     use_cache = model.config.use_cache
     model.config.use_cache = False
     model.eval()
     sequential = model.get_sequential(mode="true")
-    layers, inps, outs, layer_kwargs = _catch_inputs(model, device, _default_loader(model, n_samples, seq_len, dataloader))
+    loader = _default_loader(model, n_samples, seq_len, dataloader)
+    if dist_on:
+        loader = [loader[j] for j in parallel.sample_shard(len(loader))]     # this rank's calibration samples
+    layers, inps, outs, layer_kwargs = _catch_inputs(model, device, loader)
     n_samples = inps.shape[0]
     for i in range(len(layers)):
         layer = layers[i].to(device)
@@ -170,7 +178,7 @@ def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, da
             for j in range(n_samples):
                 layer(inps[j].unsqueeze(0), **layer_kwargs)
             handle.remove()
-            H = solvers.finalize_hessian(fq)
+            H = solvers.finalize_hessian(fq, all_reduce=dist_on)
             by_group = {}
             for name in subset:
                 wq = subset[name].weight_quantizer
@@ -187,7 +195,7 @@ def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, da
                 for n in members:
                     by_q.setdefault(solvers.quantizer_key(subset[n].weight_quantizer), []).append(n)
                 for same in by_q.values():
-                    solvers.update_weights_shared([subset[n] for n in same], device, factor, block_size=128)
+                    solvers.update_weights_shared([subset[n] for n in same], device, factor, block_size=128, shard_rows=dist_on)
                 del factor
             for name in subset:
                 del subset[name].weight_quantizer

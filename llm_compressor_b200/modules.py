@@ -12,7 +12,12 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .quantizers import FakeQuantizer
+
+# INT per-token / per-group activation quantisers in front of a bf16 Linear run as ONE kernel (ops.qlinear_forward);
+# everything else is quantizer kernel + F.linear (cuBLAS), as in the reference.  False forces the two-kernel form.
+FUSED_ACT_QDQ = True
 
 
 def bind_reference(*reference_modules):
@@ -53,6 +58,9 @@ class QLinear(nn.Linear):
         if kwargs.get("R1") is not None:
             raise NotImplementedError("online R1 / R2 rotation belongs to the SpinQuant training model (out of scope); "
                                       "rotate offline with llm_compressor_b200.hadamard.rotate_model")
+        if FUSED_ACT_QDQ and ops.qlinear_fusable(inputs, self.weight, self.input_quantizer):
+            # activation fake-quant in the operand prologue of a tcgen05 GEMM: QDQ(x) is never written to HBM
+            return self.output_quantizer(ops.qlinear_forward(inputs, self.weight, self.bias, self.input_quantizer))
         return self.output_quantizer(F.linear(self.input_quantizer(inputs), self.weight, self.bias))
 
 

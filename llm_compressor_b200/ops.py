@@ -485,3 +485,43 @@ def tgemm_nt(A, B, C=None, alpha=1.0, accumulate=False, kchain=0):
                             1 if accumulate else 0, int(kchain), _ptr(ws), ws_bytes, _stream(A.device))
     _lib.check(rc, "lcb_tgemm_nt")
     return C
+
+
+def qlinear_forward(x, weight, bias=None, quantizer=None):
+    """F.linear(quantizer(x), weight, bias) with the activation fake-quant fused into the operand prologue of a tcgen05
+    GEMM (lcb_qlinear_fwd; ref: modules/qlinear.py:86-88).  `quantizer`: an INTQuantizer along the last axis, per token
+    (group_size -1) or per group (a multiple of 64 dividing k), or None for the plain GEMM.  bf16 CUDA tensors."""
+    _need_cuda(x, weight, bias)
+    L = _lib.lib()
+    k = x.shape[-1]
+    n = weight.shape[0]
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.shape[1] == k
+    x2 = x.reshape(-1, k).contiguous()
+    m = x2.shape[0]
+    w = weight.contiguous()
+    b = bias.contiguous() if bias is not None else None
+    y = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    cfg = scales = zeros = None
+    group = k
+    if quantizer is not None:
+        scales, zeros = quantizer.find_params(x2)            # find-only pass: [m, G, 1] in x.dtype
+        group = k if quantizer.group_size in (-1, k) else int(quantizer.group_size)
+        scales = scales.reshape(m, k // group).contiguous()
+        zeros = zeros.reshape(m, k // group).contiguous()
+        cfg = ctypes.byref(quantizer._cfg())
+    with torch.cuda.device(x.device):
+        rc = L.lcb_qlinear_fwd(cfg, _ptr(x2), _ptr(w), _ptr(b), _ptr(y), m, n, k, group, _ptr(scales), _ptr(zeros),
+                               _stream(x.device))
+    _lib.check(rc, "lcb_qlinear_fwd")
+    return y.reshape(x.shape[:-1] + (n,))
+
+
+def qlinear_fusable(x, weight, quantizer):
+    """Can `F.linear(quantizer(x), weight)` run as one lcb_qlinear_fwd?"""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16):
+        return False
+    k = x.shape[-1]
+    if type(quantizer).__name__ != "INTQuantizer" or quantizer.axes != -1 or getattr(quantizer, "mse", False) or quantizer.is_profile:
+        return False
+    gs = quantizer.group_size
+    return k % 64 == 0 and (gs in (-1, k) or (isinstance(gs, int) and gs > 0 and gs % 64 == 0 and k % gs == 0))

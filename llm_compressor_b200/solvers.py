@@ -47,13 +47,17 @@ def _accumulate(holder, x, dxxt=None, x_fp=None):
         holder._h_raw = True
 
 
-def finalize_hessian(holder):
-    """Bring holder.H (and holder.dXXT) to the reference's running-mean value. Idempotent."""
+def finalize_hessian(holder, all_reduce=False):
+    """Bring holder.H (and holder.dXXT) to the reference's running-mean value. Idempotent.
+    all_reduce (sample-sharded calibration, one process per GPU): the raw per-rank sums and sample counts are summed over
+    the ranks first (parallel.reduce_hessian_), so every rank ends with the Hessian of ALL samples."""
     if getattr(holder, "_h_raw", False):
         acc = getattr(holder, "_h_acc", None)
         if acc is not None:
             acc.flush()
             del holder._h_acc
+        if all_reduce:
+            holder.nsamples = parallel.reduce_hessian_(holder.H, holder.nsamples, getattr(holder, "dXXT", None))
         scale = 2.0 / max(holder.nsamples, 1)
         ops.hessian_finalize(holder.H, scale, True)
         if getattr(holder, "dXXT", None) is not None:
@@ -133,9 +137,20 @@ def factorize(H, group_size, actorder=True, percdamp=0.01, dXXT=None, alpha=0.25
     return Factor(dead, perm, invperm, col_perm, U, P, group_size, pending, p_args)
 
 
-def _solve(q, W, factor, block_size):
+def _solve(q, W, factor, block_size, shard_rows=False):
     """GPTQ / GPTAQ solve of one weight matrix W [N, K] (rows = outputs; bf16 or fp32, not modified) with quantizer
-    q and a ready Factor; returns the dequantised result [N, K] in W's dtype and the original column order."""
+    q and a ready Factor; returns the dequantised result [N, K] in W's dtype and the original column order.
+    shard_rows (under torch.distributed, one process per GPU): every rank solves its slice of the output rows -- rows are
+    independent given U, the permutation and row-wise parameters -- and the slices are all-gathered."""
+    if shard_rows and parallel.world()[1] > 1 and type(q).__name__ != "NVFPQuantizer" and q.group_size != 0:
+        n_rows = W.shape[0]
+        mine = W[parallel.row_shard(n_rows)].contiguous()
+        if mine.shape[0] == 0:      # empty trailing shard: nothing to solve, but the collectives below still run
+            factor.resolve()
+            part = mine
+        else:
+            part = _solve(q, mine, factor, block_size)
+        return parallel.gather_rows(part, n_rows)
     N, K = W.shape
     group_size = factor.group_size
     per_col = group_size in (0, -1)
@@ -178,7 +193,7 @@ def _store_w(layer, Q):
     layer.weight.data = Q.reshape(layer.weight.shape).to(layer.weight.data.dtype).contiguous()
 
 
-def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, factor=None):
+def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, factor=None, shard_rows=False):
     q = layer.weight_quantizer
     W = _layer_w(layer)
     group_size = q.group_size  # read before find_params mutates -1 (ref: gptq/core.py:171)
@@ -189,7 +204,7 @@ def _update_weight(layer, device, block_size, percdamp, actorder, alpha=None, fa
     for attr in ("H", "dXXT"):
         if hasattr(q, attr):
             delattr(q, attr)
-    _store_w(layer, _solve(q, W, factor, block_size))
+    _store_w(layer, _solve(q, W, factor, block_size, shard_rows))
 
 
 def quantizer_key(q):
@@ -198,7 +213,7 @@ def quantizer_key(q):
             int(getattr(q, "scale_ebits", 8)), bool(getattr(q, "mse", False)))
 
 
-def update_weights_shared(layers, device, factor, block_size=128):
+def update_weights_shared(layers, device, factor, block_size=128, shard_rows=False):
     """Solve several Linears that share one Factor (q/k/v, gate/up: same input, same H) as ONE stacked
     [sum N_i, K] problem.  Rows are independent given U, the permutation and row-wise quantiser
     parameters, so the result equals calling update_weight on each layer (ref: gptq/core.py:129-137 loops
@@ -214,7 +229,7 @@ def update_weights_shared(layers, device, factor, block_size=128):
         and not any(_is_conv1d(l) for l in layers) and all(quantizer_key(l.weight_quantizer) == quantizer_key(q0) for l in layers)
     if not stackable:
         for l in layers:
-            _update_weight(l, device, block_size, 0.01, True, factor=factor)
+            _update_weight(l, device, block_size, 0.01, True, factor=factor, shard_rows=shard_rows)
         return
     sizes = [l.weight.shape[0] for l in layers]
     W = torch.cat([l.weight.data for l in layers], 0).contiguous()
@@ -222,7 +237,7 @@ def update_weights_shared(layers, device, factor, block_size=128):
         for attr in ("H", "dXXT"):
             if hasattr(l.weight_quantizer, attr):
                 delattr(l.weight_quantizer, attr)
-    Q = _solve(q0, W, factor, block_size)
+    Q = _solve(q0, W, factor, block_size, shard_rows)
     o = 0
     for l, n in zip(layers, sizes):
         _store_w(l, Q[o:o + n])

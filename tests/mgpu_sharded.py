@@ -63,10 +63,47 @@ def main():
     mr = parallel.mask_ria_sharded(W[rows].contiguous(), s, 0.5, 0.5)
     agree = float((mr == ops.mask_ria(W, s, 0.5, 0.5)[rows]).float().mean())
     assert agree > 0.9995, agree
+    # the whole GPTQ driver, sample- and row-sharded (drivers.gptq(distributed=True)), against the single-process run
+    gq = _gptq_driver_check(dev)
     dist.barrier()
     if rank == 0:
-        print("mgpu sharded ok: world", world, "ria agreement", agree)
+        print("mgpu sharded ok: world", world, "ria agreement", agree, "gptq driver identical weights", gq)
     dist.destroy_process_group()
+
+
+def _gptq_driver_check(dev):
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from llm_compressor_b200 import adapters, drivers
+
+    def model():
+        cfg = LlamaConfig(vocab_size=256, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                          num_key_value_heads=2, max_position_embeddings=128, tie_word_embeddings=False,
+                          attn_implementation="eager")
+        torch.manual_seed(0)
+        m = LlamaForCausalLM(cfg).to(torch.bfloat16)
+        g = torch.Generator().manual_seed(1)
+        m.model.embed_tokens.weight.data *= torch.exp(0.7 * torch.randn(256, generator=g)).to(torch.bfloat16)
+        return adapters.prepare(m, "int4-g[128]-rw", None)
+
+    loader = drivers.synthetic_loader(256, 16, 128, seed=0)
+    sharded = model()
+    drivers.gptq(sharded, dev, 16, 128, False, False, dataloader=loader, distributed=True)
+    single = model()
+    drivers.gptq(single, dev, 16, 128, False, False, dataloader=loader, distributed=False)
+    worst = 1.0
+    for (k, a), (_, b) in zip(sharded.state_dict().items(), single.state_dict().items()):
+        if k.endswith("proj.weight"):
+            worst = min(worst, float((a == b).float().mean()))
+    # every rank must hold the same compressed model, and it must agree with the single-process result (the Hessian sums
+    # re-associate over the ranks: codes move only where a weight sits on a rounding boundary)
+    chk = torch.stack([p.float().sum() for k, p in sharded.state_dict().items() if k.endswith("proj.weight")]).to(dev)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks disagree on the compressed model"
+    assert worst > 0.98, worst
+    return worst
 
 
 if __name__ == "__main__":

@@ -1,4 +1,5 @@
-"""Additional smoke checks: one small invocation of each stage against the CPU oracle."""
+"""TEST INFRASTRUCTURE (called by __graft_entry__.smoke()): one small invocation of each stage of the hot path on the
+GPU, checked against the CPU oracle.  Lives outside the product package because it imports oracle/."""
 import numpy as np
 import torch
 
