@@ -150,6 +150,38 @@ def fake_quant_bandwidth(lc, torch, dev, hbm_gbs):
     return out
 
 
+def fused_qlinear_times(lc, torch, dev):
+    """F.linear(input_quantizer(x), W) of one calibration forward call ([1, 2048, K] bf16 activation, int8
+    per-token and int8-g128 activation quantisers) as quantizer kernel + cuBLAS (the reference's two-op form on our
+    quantizer) against the fused lcb_qlinear_fwd (find-only pass + tcgen05 GEMM with the QDQ in its operand prologue)."""
+    import torch.nn.functional as F
+    from llm_compressor_b200 import ops
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(4)
+    for name, K, N in (("qkv_3072x5120", D_MODEL, D_MODEL + 2 * D_KV), ("gate_up_3072x16384", D_MODEL, 2 * D_FFN), ("down_8192x3072", D_FFN, D_MODEL)):
+        x = torch.randn(1, SEQ_LEN, K, generator=g, device=dev).to(torch.bfloat16)
+        W = (0.02 * torch.randn(N, K, generator=g, device=dev)).to(torch.bfloat16)
+        for gs in (-1, 128):
+            q = lc.FakeQuantizer.build(dict(type="int", format="int8", group_size=gs, axes=-1, zero_point=False, is_profile=False)).to(dev)
+            q.check_nan = False
+            res = {}
+            for key, fn in (("two_kernel_ms", lambda: F.linear(q(x), W)), ("fused_ms", lambda: ops.qlinear_forward(x, W, None, q)),
+                            ("gemm_only_cublas_ms", lambda: F.linear(x, W))):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(20):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                res[key] = a.elapsed_time(b) / 20
+            res["fused_tflops"] = 2.0 * SEQ_LEN * K * N / res["fused_ms"] / 1e9
+            out["%s_int8_%s" % (name, "token" if gs == -1 else "g128")] = res
+    return out
+
+
 def rotation_bandwidth(torch, dev, hbm_gbs):
     """randomised Hadamard rotation W @ R1 (lcb_hadamard_rows) on a [65536, n] bf16 tensor (larger than
     L2), n = 3072 (Llama-3.2-3B hidden, K = 12) and 2560 (Gemma-3 / Qwen3 hidden, K = 40).  4 B / element (read + write)."""
@@ -366,6 +398,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "hessian_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
+    fused = fused_qlinear_times(lc, torch, dev) if not args.no_fake_quant else None
     chol_cmp = cholesky_vs_cusolver(torch, dev) if not args.no_fake_quant else None
     eager = reference_eager_b200(torch, dev) if not args.no_fake_quant else None
     cpu = None
@@ -410,6 +443,7 @@ def run_ours(args):
                      "stage_share_of_step": hess_ms_total / ms},
         "fake_quant": fq,
         "hadamard_rotation": rot,
+        "fused_act_qdq_linear": fused,
         "cholesky_inverse": chol_cmp,
         "reference_eager_b200": eager,
         "result_checksum": checksum,
