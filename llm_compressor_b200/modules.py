@@ -15,9 +15,12 @@ from torch import nn
 from . import ops
 from .quantizers import FakeQuantizer
 
-# INT per-token / per-group activation quantisers in front of a bf16 Linear run as ONE kernel (ops.qlinear_forward);
-# everything else is quantizer kernel + F.linear (cuBLAS), as in the reference.  False forces the two-kernel form.
-FUSED_ACT_QDQ = True
+# True: INT per-token / per-group activation quantisers in front of a bf16 Linear run as ONE kernel (ops.qlinear_forward,
+# bit-identical output).  Default False: measured on B200 (bench.py `fused_act_qdq_linear`) the single-CTA tcgen05 GEMM of
+# lcb_qlinear_fwd reaches 0.35-0.59 PFLOP/s while quantizer kernel + cuBLAS (2-CTA tiles) runs the same call at the
+# equivalent of 0.9-1.4 PFLOP/s -- at calibration shapes the activation fits L2, so the saved HBM round trip does not pay
+# for the slower GEMM yet.
+FUSED_ACT_QDQ = False
 
 
 def bind_reference(*reference_modules):

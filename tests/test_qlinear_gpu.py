@@ -63,13 +63,18 @@ def test_qlinear_module_uses_the_fused_kernel_and_matches():
     x = torch.randn(1, 512, 1024).to(torch.bfloat16).to(DEV)
     m = modules.QLinear(lin, cfg, torch.bfloat16, op_name="t").to(DEV)
     L = _lib.lib()
-    n0 = L.lcb_launch_count()
-    y = m(x)
-    launches = L.lcb_launch_count() - n0
+    prev = modules.FUSED_ACT_QDQ
+    modules.FUSED_ACT_QDQ = True
+    try:
+        n0 = L.lcb_launch_count()
+        y = m(x)
+        launches = L.lcb_launch_count() - n0
+    finally:
+        modules.FUSED_ACT_QDQ = prev
     modules.FUSED_ACT_QDQ = False
     try:
         y2 = m(x)
     finally:
-        modules.FUSED_ACT_QDQ = True
+        modules.FUSED_ACT_QDQ = prev
     assert launches == 2                     # find-only pass + the fused GEMM
     assert float((y.float() - y2.float()).abs().max()) <= float(y2.float().abs().max()) * 2.0 ** -7
