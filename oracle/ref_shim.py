@@ -18,20 +18,23 @@ import types
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+_ZIP = os.path.join(_HERE, "_ref", "llm_compressor_ref.zip")
+
+
 def _default_root():
-    """/root/reference in the build container; on the GPU box the unmodified copy that oracle/make_ref.py left in
-    oracle/_ref/ (git-ignored, travels with the snapshot)."""
-    for cand in (os.environ.get("LC_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
-        if cand and os.path.isdir(os.path.join(cand, "llm_compressor")):
+    """/root/reference in the build container; on the GPU box the archive of unmodified reference modules that
+    oracle/make_ref.py left in oracle/_ref/ (git-ignored, travels with the snapshot; imported in place via zipimport)."""
+    for cand in (os.environ.get("LC_REFERENCE_ROOT"), "/root/reference"):
+        if cand and (os.path.isdir(os.path.join(cand, "llm_compressor")) or (cand.endswith(".zip") and os.path.isfile(cand))):
             return cand
-    return "/root/reference"
+    return _ZIP
 
 
 REF_ROOT = _default_root()
 
 
 def available():
-    return os.path.isdir(os.path.join(REF_ROOT, "llm_compressor"))
+    return os.path.isdir(os.path.join(REF_ROOT, "llm_compressor")) or (REF_ROOT.endswith(".zip") and os.path.isfile(REF_ROOT))
 
 
 def _stub(name, **attrs):

@@ -21,7 +21,7 @@ def test_reference_arm_prints_the_contract_line():
     cb = d["cpu_baseline"]
     # "reference" = the unmodified reference from oracle/_ref (or /root/reference); "port" only when neither is present
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
-    have_ref = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "llm_compressor")) or os.path.isdir("/root/reference/llm_compressor")
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "llm_compressor_ref.zip")) or os.path.isdir("/root/reference/llm_compressor")
     assert cb["kind"] == ("reference" if have_ref else "port")
     assert "workload" in d["config"] and "model" not in d["config"]
 
