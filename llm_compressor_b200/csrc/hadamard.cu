@@ -33,7 +33,7 @@ struct HadArgs {
   int n, m, K, rpc;
   int dt_in, dt_out;
   int raw_bytes;  // tiled kernel: size of the raw staging area in front of the work buffer
-  int sgn_off;    // tiled kernel: byte offset of the packed sign words
+  int sgn_off;    // tiled kernel: byte offset of the row of sign XOR masks
   double divisor;  // the reference divides by float32(sqrt(n)) (hadamard_utils.py:111)
   double rcp;      // 1 / divisor
   unsigned long long hk[HAD_MAXK];  // bit a of hk[a'] set  <=>  H_K[a'][a] == -1
@@ -233,17 +233,43 @@ constexpr unsigned long long paley1_row_mask(int K, int r) {
   return m;
 }
 
-template <typename Acc, int KB, int R>
-__device__ __forceinline__ Acc paley_dot(const Acc (&v)[KB]) {
-  constexpr unsigned long long M = paley1_row_mask(KB, R);
-  Acc acc = ((M & 1ull) ? -v[0] : v[0]);
+// H_K v for a Paley-I matrix, K = 4 G: the entries are +-1, so within a group of four inputs (a, b, c, d) every row needs
+// one of the eight values a +- b +- c +- d (up to an overall sign).  Build those once per group (12 adds) and each output
+// is a signed sum of G of them: 12 G + K (G - 1) adds instead of K (K - 1) -- 60 instead of 132 for H_12, 140 instead of
+// 380 for H_20.  Signs and indices fold at compile time (the masks are constexpr, the loops fully unrolled).
+template <typename Acc, int KB>
+__device__ __forceinline__ void paley_groups(const Acc (&v)[KB], Acc (&cmb)[KB / 4][8]) {
 #pragma unroll
-  for (int c = 1; c < KB; ++c) acc = ((M >> c) & 1ull) ? acc - v[c] : acc + v[c];
+  for (int g = 0; g < KB / 4; ++g) {
+    const Acc a = v[4 * g], b = v[4 * g + 1], c = v[4 * g + 2], d = v[4 * g + 3];
+    const Acc s0 = a + b, d0 = a - b, s1 = c + d, d1 = c - d;
+    cmb[g][0] = s0 + s1; cmb[g][1] = d0 + s1;   // index = [b negative] + 2 * (2 * [c negative] + [d negative])
+    cmb[g][2] = s0 + d1; cmb[g][3] = d0 + d1;
+    cmb[g][4] = s0 - d1; cmb[g][5] = d0 - d1;
+    cmb[g][6] = s0 - s1; cmb[g][7] = d0 - s1;
+  }
+}
+template <typename Acc, int KB, int R>
+__device__ __forceinline__ Acc paley_dot(const Acc (&cmb)[KB / 4][8]) {
+  constexpr unsigned long long M = paley1_row_mask(KB, R);
+  Acc acc = 0;
+#pragma unroll
+  for (int g = 0; g < KB / 4; ++g) {
+    const unsigned m4 = (unsigned)((M >> (4 * g)) & 0xFull);
+    const bool flip = (m4 & 1u) != 0;                       // a enters negated: use the mirrored pattern, negated
+    const unsigned q = flip ? (m4 ^ 0xFu) : m4;
+    const int idx = (int)((q >> 1) & 1u) + 2 * (int)(2 * ((q >> 2) & 1u) + ((q >> 3) & 1u));
+    const Acc t = cmb[g][idx];
+    if (g == 0) acc = flip ? -t : t;
+    else acc = flip ? acc - t : acc + t;
+  }
   return acc;
 }
 template <typename Acc, int KB, int... Rs>
-__device__ __forceinline__ void paley_store(const Acc (&v)[KB], Acc* sm, int sbase, int m, std::integer_sequence<int, Rs...>) {
-  ((sm[pad32(sbase + (Rs << m))] = paley_dot<Acc, KB, Rs>(v)), ...);
+__device__ __forceinline__ void paley_store(const Acc (&v)[KB], Acc* p, int pstride, std::integer_sequence<int, Rs...>) {
+  Acc cmb[KB / 4][8];
+  paley_groups<Acc, KB>(v, cmb);
+  ((p[Rs * pstride] = paley_dot<Acc, KB, Rs>(cmb)), ...);
 }
 
 template <typename Acc, typename TIn>
@@ -276,9 +302,9 @@ __device__ __forceinline__ void store16_out(void* y, int dt, int64_t e0, const A
     uint32_t w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const __nv_bfloat16 lo = __float2bfloat16_rn((float)(v[2 * i] * rcp));      // torch: double -> float -> bf16
-      const __nv_bfloat16 hi = __float2bfloat16_rn((float)(v[2 * i + 1] * rcp));
-      w[i] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+      // torch: double -> float -> bf16; one packed cvt.rn.bf16x2.f32 per pair
+      const __nv_bfloat162 pr = __floats2bfloat162_rn((float)(v[2 * i] * rcp), (float)(v[2 * i + 1] * rcp));
+      w[i] = *reinterpret_cast<const uint32_t*>(&pr);
     }
     uint4* p = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + e0);
     p[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -297,11 +323,15 @@ __device__ __forceinline__ void store16_out(void* y, int dt, int64_t e0, const A
   }
 }
 
+// Shape known at compile time (NC = n, B0C = first bit of a pass) for the common widths: strides become immediates and
+// the per-group index arithmetic folds; NC == 0 / B0C == 0 take the values from the arguments.
 // radix-2 stages on bits [b0, b0 + R), b0 >= 5: N = 2^R values per thread at a constant padded stride
-template <typename Acc, typename TIn, int R, bool SRC_RAW>
-__device__ __forceinline__ void mid_bits(const HadArgs& a, const unsigned char* raw, Acc* sm, int nr, int b0) {
+template <typename Acc, typename TIn, int R, bool SRC_RAW, int NC = 0, int B0C = 0>
+__device__ __forceinline__ void mid_bits(const HadArgs& a, const unsigned char* raw, Acc* sm, int nr, int b0_rt) {
   constexpr int N = 1 << R;
-  const int groups = (nr * a.n) >> R;
+  const int n = NC > 0 ? NC : a.n;
+  const int b0 = B0C > 0 ? B0C : b0_rt;
+  const int groups = (nr * n) >> R;
   const int lomask = (1 << b0) - 1;
   const int step = 1 << b0, pstep = step + (step >> 5);
   for (int g = threadIdx.x; g < groups; g += HAD_THREADS) {
@@ -320,9 +350,10 @@ __device__ __forceinline__ void mid_bits(const HadArgs& a, const unsigned char* 
 }
 
 // the lowest 5 bits: 32 contiguous values per thread, straight to global memory
-template <typename Acc, typename TIn, bool SRC_RAW>
+template <typename Acc, typename TIn, bool SRC_RAW, int NC = 0>
 __device__ __forceinline__ void low_bits_out(const HadArgs& a, const unsigned char* raw, const Acc* sm, int64_t row0, int nr) {
-  const int groups = (nr * a.n) >> 5;
+  const int n = NC > 0 ? NC : a.n;
+  const int groups = (nr * n) >> 5;
   for (int g = threadIdx.x; g < groups; g += HAD_THREADS) {
     Acc v[32];
 #pragma unroll
@@ -334,125 +365,206 @@ __device__ __forceinline__ void low_bits_out(const HadArgs& a, const unsigned ch
     Acc lo[16], hi[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { lo[j] = v[j]; hi[j] = v[16 + j]; }
-    const int64_t e0 = row0 * (int64_t)a.n + 32 * g;
+    const int64_t e0 = row0 * (int64_t)n + 32 * g;
     store16_out<Acc>(a.y, a.dt_out, e0, lo, a.divisor, a.rcp);
     store16_out<Acc>(a.y, a.dt_out, e0 + 16, hi, a.divisor, a.rcp);
   }
 }
 
-// H_K across the leading index (stride L = 2^m), raw tile -> work buffer
-template <typename Acc, typename TIn, int KT>
+// H_K across the leading index (stride L = 2^m), raw tile -> work buffer.  L >= 32, so the padded index of
+// sbase + r L is pad32(sbase) + r (L + L / 32): one base address and a constant stride per thread.
+template <typename Acc, typename TIn, int KT, int MC = 0>
 __device__ __forceinline__ void hadk_first(const HadArgs& a, const unsigned char* raw, Acc* sm, int nr) {
-  const int L = 1 << a.m;
+  const int m = MC > 0 ? MC : a.m;
+  const int n = MC > 0 ? (KT << MC) : a.n;
+  const int L = 1 << m;
+  const int pstride = L + (L >> 5);
   for (int q = threadIdx.x; q < nr * L; q += HAD_THREADS) {
-    const int row = q >> a.m, b = q & (L - 1);
-    const int sbase = row * a.n + b;
+    const int row = q >> m, b = q & (L - 1);
+    const int sbase = row * n + b;
+    const TIn* rp = reinterpret_cast<const TIn*>(raw) + sbase;
+    Acc* wp = sm + pad32(sbase);
     if constexpr (KT == 12) {
       Acc v[12];
 #pragma unroll
-      for (int c = 0; c < 12; ++c) v[c] = raw_at<Acc, TIn>(raw, sbase + (c << a.m));
-      paley_store<Acc, 12>(v, sm, sbase, a.m, std::make_integer_sequence<int, 12>{});
+      for (int c = 0; c < 12; ++c) v[c] = raw_at<Acc, TIn>(reinterpret_cast<const unsigned char*>(rp), c * L);
+      paley_store<Acc, 12>(v, wp, pstride, std::make_integer_sequence<int, 12>{});
     } else if constexpr (KT == 40) {
       Acc v0[20], v1[20];
 #pragma unroll
       for (int c = 0; c < 20; ++c) {
-        const Acc p = raw_at<Acc, TIn>(raw, sbase + (c << a.m)), r = raw_at<Acc, TIn>(raw, sbase + ((c + 20) << a.m));
+        const Acc p = raw_at<Acc, TIn>(reinterpret_cast<const unsigned char*>(rp), c * L);
+        const Acc r = raw_at<Acc, TIn>(reinterpret_cast<const unsigned char*>(rp), (c + 20) * L);
         v0[c] = p + r;
         v1[c] = p - r;
       }
-      paley_store<Acc, 20>(v0, sm, sbase, a.m, std::make_integer_sequence<int, 20>{});
-      paley_store<Acc, 20>(v1, sm, sbase + (20 << a.m), a.m, std::make_integer_sequence<int, 20>{});
+      paley_store<Acc, 20>(v0, wp, pstride, std::make_integer_sequence<int, 20>{});
+      paley_store<Acc, 20>(v1, wp + 20 * pstride, pstride, std::make_integer_sequence<int, 20>{});
     }
   }
 }
 
-template <typename Acc, typename TIn, int KT>
+// bits [5, TOP) in register-blocked passes from the top down (the schedule of the run-time loop below, unrolled at
+// compile time when the shape is a template argument)
+constexpr int pass_bits(int top) {
+  const int hi = top - 5;
+  int r = hi % 5;
+  if (r == 0) r = 5;
+  if (hi > 5 && hi < 10) r = (hi + 1) / 2;  // 6..9 -> two balanced passes
+  return r;
+}
+template <typename Acc, typename TIn, int NC, int TOP, bool FROM_RAW>
+__device__ __forceinline__ void passes_ct(const HadArgs& a, const unsigned char* raw, Acc* sm, int64_t row0, int nr) {
+  if constexpr (TOP > 5) {
+    constexpr int R = pass_bits(TOP);
+    mid_bits<Acc, TIn, R, FROM_RAW, NC, TOP - R>(a, raw, sm, nr, TOP - R);
+    __syncthreads();
+    passes_ct<Acc, TIn, NC, TOP - R, false>(a, raw, sm, row0, nr);
+  } else {
+    low_bits_out<Acc, TIn, FROM_RAW, NC>(a, raw, sm, row0, nr);
+  }
+}
+
+// MC > 0: n = KT * 2^MC is a compile-time shape (the common hidden sizes); MC == 0: any m >= 5 at run time
+template <typename Acc, typename TIn, int KT, int MC>
 __global__ void __launch_bounds__(HAD_THREADS, sizeof(Acc) == 4 ? 4 : 2) hadamard_tile_kernel(const __grid_constant__ HadArgs a) {
   extern __shared__ __align__(16) unsigned char had_smem[];
   unsigned char* raw = had_smem;
   Acc* sm = reinterpret_cast<Acc*>(had_smem + a.raw_bytes);
-  uint32_t* sgn = reinterpret_cast<uint32_t*>(had_smem + a.sgn_off);  // n / 32 words, bit set <=> sign < 0
-  constexpr int EPV = 16 / (int)sizeof(TIn);                          // elements per 16-byte vector
+  uint4* sgn = reinterpret_cast<uint4*>(had_smem + a.sgn_off);  // one row of XOR masks (sign bit set <=> sign < 0), raw layout
+  constexpr int EPV = 16 / (int)sizeof(TIn);                    // elements per 16-byte vector
+  const int nvec_row = (MC > 0 ? (KT << MC) : a.n) / EPV;
   if (a.signs != nullptr) {
-    for (int i = threadIdx.x; i < a.n; i += HAD_THREADS) {  // n % 32 == 0 is not guaranteed: n % 16 == 0 is
-      const unsigned bal = __ballot_sync(__activemask(), a.signs[i] < 0.0f);
-      if ((threadIdx.x & 31) == 0) sgn[i >> 5] = bal;
+    for (int i = threadIdx.x; i < nvec_row; i += HAD_THREADS) {
+      uint32_t w[4];
+      if constexpr (EPV == 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          w[q] = (a.signs[i * 8 + 2 * q] < 0.0f ? 0x8000u : 0u) | (a.signs[i * 8 + 2 * q + 1] < 0.0f ? 0x80000000u : 0u);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = a.signs[i * 4 + q] < 0.0f ? 0x80000000u : 0u;
+      }
+      sgn[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
   __syncthreads();
-  for (int64_t row0 = (int64_t)blockIdx.x * a.rpc; row0 < a.rows; row0 += (int64_t)gridDim.x * a.rpc) {
+  int v0 = threadIdx.x;   // vector index within a row of the first vector this thread stages
+  while (v0 >= nvec_row) v0 -= nvec_row;
+  int vstep = HAD_THREADS;
+  while (vstep >= nvec_row) vstep -= nvec_row;   // HAD_THREADS mod nvec_row
+  const int64_t stride_rows = (int64_t)gridDim.x * a.rpc;
+  // The raw tile of the NEXT iteration is fetched with cp.async as soon as the last reader of the current one is done
+  // (the H_K stage, or the first radix-2 pass when K == 1): the HBM latency hides under the remaining passes.
+  auto fetch = [&](int64_t r0) {
+    if (r0 >= a.rows) return;
+    const int cnt = (int)min((int64_t)a.rpc, a.rows - r0) * nvec_row;
+    const uint4* src = reinterpret_cast<const uint4*>(static_cast<const TIn*>(a.x) + r0 * (int64_t)a.n);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw);
+    for (int i = threadIdx.x; i < cnt; i += HAD_THREADS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+  };
+  fetch((int64_t)blockIdx.x * a.rpc);
+  for (int64_t row0 = (int64_t)blockIdx.x * a.rpc; row0 < a.rows; row0 += stride_rows) {
     const int nr = (int)min((int64_t)a.rpc, a.rows - row0);
-    {  // stage the raw tile (one contiguous chunk, 16-byte vectors) with the signs applied to the sign bits
-      const uint4* src = reinterpret_cast<const uint4*>(static_cast<const TIn*>(a.x) + row0 * (int64_t)a.n);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (a.signs != nullptr) {  // the signs go into the sign bits in place; every thread touches only the vectors it fetched
       uint4* dst = reinterpret_cast<uint4*>(raw);
-      const int nvec = (nr * a.n) / EPV;
+      const int nvec = nr * nvec_row;
+      int v = v0;
       for (int i = threadIdx.x; i < nvec; i += HAD_THREADS) {
-        uint4 t = __ldg(src + i);
-        if (a.signs != nullptr) {
-          const int e = (i * EPV) % a.n;
-          const uint32_t bits = sgn[e >> 5] >> (e & 31);
-          if constexpr (EPV == 8) {
-            t.x ^= ((bits & 1u) << 15) | ((bits & 2u) << 30);
-            t.y ^= ((bits & 4u) << 13) | ((bits & 8u) << 28);
-            t.z ^= ((bits & 16u) << 11) | ((bits & 32u) << 26);
-            t.w ^= ((bits & 64u) << 9) | ((bits & 128u) << 24);
-          } else {
-            t.x ^= (bits & 1u) << 31;
-            t.y ^= (bits & 2u) << 30;
-            t.z ^= (bits & 4u) << 29;
-            t.w ^= (bits & 8u) << 28;
-          }
-        }
+        uint4 t = dst[i];
+        const uint4 mk = sgn[v];
+        t.x ^= mk.x; t.y ^= mk.y; t.z ^= mk.z; t.w ^= mk.w;
         dst[i] = t;
+        v += vstep;
+        if (v >= nvec_row) v -= nvec_row;
       }
     }
     __syncthreads();
-    bool from_raw = true;
-    if constexpr (KT > 1) {
-      hadk_first<Acc, TIn, KT>(a, raw, sm, nr);
-      __syncthreads();
-      from_raw = false;
-    }
-    int top = a.m;  // bits [5, top) are still to do
-    while (top > 5) {
-      const int hi = top - 5;
-      int r = hi % 5;
-      if (r == 0) r = 5;
-      if (hi > 5 && hi < 10) r = (hi + 1) / 2;  // 6..9 -> two balanced passes
-      const int b0 = top - r;
+    if constexpr (MC > 0) {
+      if constexpr (KT > 1) {
+        hadk_first<Acc, TIn, KT, MC>(a, raw, sm, nr);
+        __syncthreads();
+        fetch(row0 + stride_rows);
+        passes_ct<Acc, TIn, (KT << MC), MC, false>(a, raw, sm, row0, nr);
+      } else if constexpr (MC > 5) {
+        constexpr int R = pass_bits(MC);
+        mid_bits<Acc, TIn, R, true, (KT << MC), MC - R>(a, raw, sm, nr, MC - R);
+        __syncthreads();
+        fetch(row0 + stride_rows);
+        passes_ct<Acc, TIn, (KT << MC), MC - R, false>(a, raw, sm, row0, nr);
+      } else {
+        low_bits_out<Acc, TIn, true, (KT << MC)>(a, raw, sm, row0, nr);
+        __syncthreads();
+        fetch(row0 + stride_rows);
+      }
+    } else {
+      bool from_raw = true;
+      if constexpr (KT > 1) {
+        hadk_first<Acc, TIn, KT>(a, raw, sm, nr);
+        __syncthreads();
+        fetch(row0 + stride_rows);
+        from_raw = false;
+      }
+      int top = a.m;  // bits [5, top) are still to do
+      while (top > 5) {
+        const int r = pass_bits(top);
+        const int b0 = top - r;
 #define LCB_HAD_PASS(RR)                                                        \
   case RR:                                                                      \
     if (from_raw) mid_bits<Acc, TIn, RR, true>(a, raw, sm, nr, b0);             \
     else mid_bits<Acc, TIn, RR, false>(a, raw, sm, nr, b0);                     \
     break;
-      switch (r) {
-        LCB_HAD_PASS(1) LCB_HAD_PASS(2) LCB_HAD_PASS(3) LCB_HAD_PASS(4) LCB_HAD_PASS(5)
-      }
+        switch (r) {
+          LCB_HAD_PASS(1) LCB_HAD_PASS(2) LCB_HAD_PASS(3) LCB_HAD_PASS(4) LCB_HAD_PASS(5)
+        }
 #undef LCB_HAD_PASS
-      __syncthreads();
-      from_raw = false;
-      top = b0;
+        __syncthreads();
+        if (from_raw) fetch(row0 + stride_rows);
+        from_raw = false;
+        top = b0;
+      }
+      if (from_raw) {
+        low_bits_out<Acc, TIn, true>(a, raw, sm, row0, nr);
+        __syncthreads();
+        fetch(row0 + stride_rows);
+      } else {
+        low_bits_out<Acc, TIn, false>(a, raw, sm, row0, nr);
+      }
     }
-    if (from_raw) low_bits_out<Acc, TIn, true>(a, raw, sm, row0, nr);
-    else low_bits_out<Acc, TIn, false>(a, raw, sm, row0, nr);
-    __syncthreads();  // the next tile overwrites raw / sm
+    __syncthreads();  // the next tile overwrites sm
   }
 }
 
-template <typename Acc, typename TIn, int KT>
+template <typename Acc, typename TIn, int KT, int MC = 0>
 int launch_tile(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
-  LCB_CUDA(cudaFuncSetAttribute(hadamard_tile_kernel<Acc, TIn, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  hadamard_tile_kernel<Acc, TIn, KT><<<grid, HAD_THREADS, smem, st>>>(a);
+  LCB_CUDA(cudaFuncSetAttribute(hadamard_tile_kernel<Acc, TIn, KT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hadamard_tile_kernel<Acc, TIn, KT, MC><<<grid, HAD_THREADS, smem, st>>>(a);
   LCB_LAUNCH_CHECK();
   return LCB_OK;
 }
 
 template <typename Acc, typename TIn>
 int launch_tile_k(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
+  // compile-time shapes: the hidden / head / intermediate sizes of the reference's model zoo (3072 = 12 * 2^8,
+  // 2560 = 40 * 2^6, 128, 1024, 2048, 4096, 8192); everything else runs the same kernel with run-time strides
   switch (a.K) {
-    case 1: return launch_tile<Acc, TIn, 1>(a, grid, smem, st);
-    case 12: return launch_tile<Acc, TIn, 12>(a, grid, smem, st);
-    default: return launch_tile<Acc, TIn, 40>(a, grid, smem, st);
+    case 1:
+      switch (a.m) {
+        case 7: return launch_tile<Acc, TIn, 1, 7>(a, grid, smem, st);
+        case 10: return launch_tile<Acc, TIn, 1, 10>(a, grid, smem, st);
+        case 11: return launch_tile<Acc, TIn, 1, 11>(a, grid, smem, st);
+        case 12: return launch_tile<Acc, TIn, 1, 12>(a, grid, smem, st);
+        case 13: return launch_tile<Acc, TIn, 1, 13>(a, grid, smem, st);
+        default: return launch_tile<Acc, TIn, 1>(a, grid, smem, st);
+      }
+    case 12:
+      if (a.m == 8) return launch_tile<Acc, TIn, 12, 8>(a, grid, smem, st);
+      return launch_tile<Acc, TIn, 12>(a, grid, smem, st);
+    default:
+      if (a.m == 6) return launch_tile<Acc, TIn, 40, 6>(a, grid, smem, st);
+      return launch_tile<Acc, TIn, 40>(a, grid, smem, st);
   }
 }
 
@@ -523,7 +635,7 @@ extern "C" int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype
     const int64_t tile = rpc * n;
     const size_t raw_bytes = (size_t)((tile * esz_in + 15) / 16 * 16);
     const size_t work_bytes = (size_t)((tile + (tile >> 5) + 16) * esz + 15) / 16 * 16;
-    const size_t smem = raw_bytes + work_bytes + (size_t)(n / 32 + 2) * 4;
+    const size_t smem = raw_bytes + work_bytes + (size_t)(n * esz_in + 15) / 16 * 16;   // + one row of sign masks
     if (smem <= 220 * 1024) {
       a.rpc = (int)rpc;
       a.raw_bytes = (int)raw_bytes;
