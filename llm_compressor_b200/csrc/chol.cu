@@ -718,6 +718,7 @@ struct TileArgs {
   unsigned long long* trace;  // debug (LCB_CHOL_TRACE=1): per task {type|i|c, t_fetch, t_acc, t_diag_flag, t_factor, t_end} in ns
   int64_t ld;
   int k, nblk, c0, c1, with_inv, ntasks;
+  int fi_nt;         // T-worker warps of factor_invert_split (1..6); 0 = the joint-worker factor_invert_la (A/B runs)
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -981,6 +982,268 @@ __device__ __forceinline__ void factor_invert_la(float* T, float* W, float* Pn, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Split-role variant of factor_invert_la (the default).  In factor_invert_la every worker does its share of BOTH trailing
+// updates (T, the factor, and W, the inverse riding along) and all of them meet at the end of each step, so the
+// pivot chain waits for the inverse's work too: 3400 cycles per 8-column step where the chain itself needs ~1300.
+// Here the inverse is taken OFF the pivot chain:
+//   warp 0            chain warp, as above;
+//   warps 1 .. nt     T workers: panel solve + trailing update of the factor only (what the next pivots wait for);
+//   warps nt+1 .. 7   W workers: row panel of the inverse W_p = Dinv W_p and its trailing update W(i,:) -= L(i,p) W_p.
+// The W workers only CONSUME what the other two groups produce (Dinv(p) and the panel L(:, p)); every step's panel and
+// Dinv get their own buffer (16 panels = 64 KB), so the factor side never waits for the inverse.  The hand-over is a
+// shared-memory counter (fence + atomicAdd by the producers' lane 0, volatile poll by the consumers): named barriers
+// cannot express a producer that runs several steps ahead.  Inside a group the steps are ordered by named barriers.
+constexpr int FS_PN_FLOATS = 16 * 8 * NB;
+constexpr int FS_SMEM_FLOATS = 2 * FI_T_FLOATS + FS_PN_FLOATS + 2 * 8 * NB + 16 * 64 + 8;
+enum { FS_BAR_TEND = 4, FS_BAR_WSYNC = 10 };   // P1 / P1B / LA / P3A keep the ids of factor_invert_la
+
+__device__ __forceinline__ void fs_signal(int* cnt, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicAdd(cnt, 1);
+  }
+}
+
+__device__ __forceinline__ void factor_invert_split(float* T, float* W, float* Pn, float* Wp, float* D, int* cnt, bool& bad,
+                                                    int tid, int nt, long long* dbg = nullptr) {
+#define FS_DBG(slot) do { if (dbg) dbg[p * 12 + (slot)] = clock64(); } while (0)
+  const int TTH = 32 * nt;             // T workers
+  const int WTH = 224 - TTH;           // W workers
+  const int CT = 32 + TTH;             // chain + T workers: participants of P1 / LA / P3A
+  for (int q = tid; q < FI_NT; q += 256) {
+    int ti, tk;
+    tri_index(q, ti, tk);
+    const float dg = (ti == tk) ? 1.0f : 0.0f;
+    *reinterpret_cast<float4*>(W + 0 * FI_PLANE + 4 * q) = make_float4(dg, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(W + 1 * FI_PLANE + 4 * q) = make_float4(0.f, dg, 0.f, 0.f);
+    *reinterpret_cast<float4*>(W + 2 * FI_PLANE + 4 * q) = make_float4(0.f, 0.f, dg, 0.f);
+    *reinterpret_cast<float4*>(W + 3 * FI_PLANE + 4 * q) = make_float4(0.f, 0.f, 0.f, dg);
+  }
+  if (tid == 0) *cnt = 0;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    // ======================================================================= chain warp
+#pragma unroll 1
+    for (int p = 0; p < 16; ++p) {
+      float* Dv = D + p * 64;            // Dinv of this step, row-major 8 x 8
+      float* Pp = Pn + p * 8 * NB;
+      if (lane == 0) FS_DBG(0);
+      if (lane == 0) {
+        float d[8][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(fi_row(T, 2 * p, 2 * p, i));
+          const float4 b = *reinterpret_cast<const float4*>(fi_row(T, 2 * p + 1, 2 * p, i));
+          const float4 c = *reinterpret_cast<const float4*>(fi_row(T, 2 * p + 1, 2 * p + 1, i));
+          d[i][0] = a.x; d[i][1] = a.y; d[i][2] = a.z; d[i][3] = a.w;
+          d[i][4] = 0.f; d[i][5] = 0.f; d[i][6] = 0.f; d[i][7] = 0.f;
+          d[i + 4][0] = b.x; d[i + 4][1] = b.y; d[i + 4][2] = b.z; d[i + 4][3] = b.w;
+          d[i + 4][4] = c.x; d[i + 4][5] = c.y; d[i + 4][6] = c.z; d[i + 4][7] = c.w;
+        }
+        float rl[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float dv = d[jj][jj];
+          if (!(dv > 0.0f)) bad = true;
+          float r = rsqrtf(dv);
+          r = fmaf(r, fmaf(-0.5f * dv * r, r, 0.5f), r);
+          rl[jj] = r;
+#pragma unroll
+          for (int i = jj + 1; i < 8; ++i) d[i][jj] *= r;
+#pragma unroll
+          for (int c = jj + 1; c < 8; ++c)
+#pragma unroll
+            for (int i = c; i < 8; ++i) d[i][c] = fmaf(-d[i][jj], d[c][jj], d[i][c]);
+        }
+        float di[8][8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) di[i][jj] = 0.0f;
+          di[jj][jj] = rl[jj];
+#pragma unroll
+          for (int i = jj + 1; i < 8; ++i) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int m = jj; m < i; ++m) sacc = fmaf(d[i][m], di[m][jj], sacc);
+            di[i][jj] = -sacc * rl[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          *reinterpret_cast<float4*>(Dv + 8 * i) = make_float4(di[i][0], di[i][1], di[i][2], di[i][3]);
+          *reinterpret_cast<float4*>(Dv + 8 * i + 4) = make_float4(di[i][4], di[i][5], di[i][6], di[i][7]);
+        }
+      }
+      __syncwarp();
+      nbar_arrive((p & 1) ? FI_BAR_P1B : FI_BAR_P1, CT);
+      if (lane == 0) FS_DBG(1);
+      if (p < 15) {
+        if (p >= 1) nbar_sync(FI_BAR_P3A, CT);   // T(p+1,p) and T(p+1,p+1) carry the updates of steps < p
+        if (lane == 0) FS_DBG(2);
+        const int r = lane >> 2, cg = lane & 3;          // row r of the 8, columns 2 cg and 2 cg + 1
+        const int gi = 8 * (p + 1) + r;
+        const float4 x0 = *reinterpret_cast<const float4*>(fi_row(T, gi >> 2, 2 * p, gi & 3));
+        const float4 x1 = *reinterpret_cast<const float4*>(fi_row(T, gi >> 2, 2 * p + 1, gi & 3));
+        const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = 2 * cg + q;
+          const float4 d0 = *reinterpret_cast<const float4*>(Dv + 8 * c), d1 = *reinterpret_cast<const float4*>(Dv + 8 * c + 4);
+          float acc = xr[0] * d0.x;                       // Dinv[c][m] == 0 for m > c
+          acc = fmaf(xr[1], d0.y, acc); acc = fmaf(xr[2], d0.z, acc); acc = fmaf(xr[3], d0.w, acc);
+          acc = fmaf(xr[4], d1.x, acc); acc = fmaf(xr[5], d1.y, acc); acc = fmaf(xr[6], d1.z, acc); acc = fmaf(xr[7], d1.w, acc);
+          Pp[c * NB + gi] = acc;
+        }
+        fs_signal(cnt, lane);            // Dinv(p) + the chain's 8 rows of panel p -> W workers (includes a __syncwarp)
+        {
+          float li[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) li[m] = Pp[m * NB + gi];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = 2 * cg + q;
+            if (c <= r) {
+              const int gc = 8 * (p + 1) + c;
+              float acc = 0.f;
+#pragma unroll
+              for (int m = 0; m < 8; ++m) acc = fmaf(li[m], Pp[m * NB + gc], acc);
+              float* e = fi_row(T, gi >> 2, gc >> 2, gi & 3) + (gc & 3);
+              *e -= acc;
+            }
+          }
+        }
+        __syncwarp();
+        nbar_arrive(FI_BAR_LA, CT);
+        if (lane == 0) FS_DBG(3);
+      } else {
+        fs_signal(cnt, lane);
+      }
+    }
+  } else if (warp <= nt) {
+    // ======================================================================= T workers
+    const int tw = tid - 32;   // 0 .. TTH - 1
+#pragma unroll 1
+    for (int p = 0; p < 16; ++p) {
+      const float* Dv = D + p * 64;
+      float* Pp = Pn + p * 8 * NB;
+      nbar_sync((p & 1) ? FI_BAR_P1B : FI_BAR_P1, CT);
+      if (tw == 0) FS_DBG(4);
+      if (8 * (p + 2) < NB) {  // ---- panel solve for the rows below the chain warp's 8
+        float dv[8][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 d0 = *reinterpret_cast<const float4*>(Dv + 8 * c), d1 = *reinterpret_cast<const float4*>(Dv + 8 * c + 4);
+          dv[c][0] = d0.x; dv[c][1] = d0.y; dv[c][2] = d0.z; dv[c][3] = d0.w;
+          dv[c][4] = d1.x; dv[c][5] = d1.y; dv[c][6] = d1.z; dv[c][7] = d1.w;
+        }
+        for (int i = 8 * (p + 2) + tw; i < NB; i += TTH) {
+          const float4 x0 = *reinterpret_cast<const float4*>(fi_row(T, i >> 2, 2 * p, i & 3));
+          const float4 x1 = *reinterpret_cast<const float4*>(fi_row(T, i >> 2, 2 * p + 1, i & 3));
+          const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m <= c; ++m) acc = fmaf(xr[m], dv[c][m], acc);
+            Pp[c * NB + i] = acc;
+          }
+        }
+      }
+      fs_signal(cnt, lane);              // this warp's rows of panel p -> W workers
+      if (tw == 0) FS_DBG(5);
+      if (p < 15) {
+        nbar_sync(FI_BAR_LA, CT);        // every panel entry of this step (T workers' and the chain warp's) is written
+        // ---- trailing micro-tiles of the factor: lower triangle from micro-row 2(p+1), minus the next diagonal tile
+        // (items 0..2: the chain warp updated it itself)
+        const int base = 2 * (p + 1);
+        const int g = 32 - base;
+        const int total = ((g * (g + 1)) >> 1) - 3;
+        if (tw == 0) FS_DBG(6);
+        bool first = true;
+        for (int it = tw; it < total || first; it += TTH) {
+          if (it < total) {
+            int u, v;
+            tri_index(it + 3, u, v);
+            fi_tile_update(T, fi_tidx(base + u, base + v), Pp, Pp, base + u, base + v);
+          }
+          if (first) {
+            first = false;
+            if (p < 14) nbar_arrive(FI_BAR_P3A, CT);   // items 0..6 (the chain warp's next inputs) are in the first round
+            if (tw == 0) FS_DBG(7);
+          }
+        }
+      }
+      if (tw == 0) FS_DBG(8);
+      nbar_sync(FS_BAR_TEND, TTH);
+    }
+  } else {
+    // ======================================================================= W workers
+    const int ww = tid - 32 - TTH;   // 0 .. WTH - 1
+    const int need_per_step = 1 + nt;
+#pragma unroll 1
+    for (int p = 0; p < 16; ++p) {
+      const float* Dv = D + p * 64;
+      const float* Pp = Pn + p * 8 * NB;
+      float* Wq = Wp + (p & 1) * 8 * NB;
+      if (lane == 0) {
+        const volatile int* vc = cnt;
+        const int need = need_per_step * (p + 1);
+        while (*vc < need) __nanosleep(32);
+        __threadfence_block();
+      }
+      __syncwarp();
+      if (ww == 0) FS_DBG(9);
+      {  // ---- row panel p of the inverse: W_p = Dinv W_p (column `col` of the 8 rows), final
+        float dv[8][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 d0 = *reinterpret_cast<const float4*>(Dv + 8 * c), d1 = *reinterpret_cast<const float4*>(Dv + 8 * c + 4);
+          dv[c][0] = d0.x; dv[c][1] = d0.y; dv[c][2] = d0.z; dv[c][3] = d0.w;
+          dv[c][4] = d1.x; dv[c][5] = d1.y; dv[c][6] = d1.z; dv[c][7] = d1.w;
+        }
+        for (int col = ww; col < 8 * p + 8; col += WTH) {
+          float w[8];
+          const int tk = col >> 2, cc = col & 3;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int rr = 8 * p + m;
+            w[m] = (tk <= (rr >> 2)) ? fi_row(W, rr >> 2, tk, rr & 3)[cc] : 0.0f;
+          }
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q <= m; ++q) acc = fmaf(dv[m][q], w[q], acc);
+            const int rr = 8 * p + m;
+            if (tk <= (rr >> 2)) fi_row(W, rr >> 2, tk, rr & 3)[cc] = acc;
+            Wq[m * NB + col] = acc;
+          }
+        }
+      }
+      nbar_sync(FS_BAR_WSYNC, WTH);
+      if (p < 15) {
+        // ---- trailing micro-tiles of the inverse: micro-rows >= 2(p+1), micro-columns <= 2p+1
+        const int base = 2 * (p + 1);
+        const int g = 32 - base;
+        const int total = g * base;
+        const float rbase = 1.0f / (float)base;
+        for (int it = ww; it < total; it += WTH) {
+          const int u = (int)(((float)it + 0.5f) * rbase), v = it - u * base;   // exact: (it + 0.5) / base is >= 1/60 away from an integer
+          fi_tile_update(W, fi_tidx(base + u, v), Pp, Wq, base + u, v);
+        }
+        nbar_sync(FS_BAR_WSYNC, WTH);
+      }
+      if (ww == 0) FS_DBG(10);
+    }
+  }
+  __syncthreads();
+#undef FS_DBG
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Tensor-core variant of the tile tasks: the same task graph, but every 128 x 128 x 128 product runs as 3xTF32
 // tcgen05.mma (M = N = 128, K = 8) with the accumulator in TMEM.  The [128][32] operand chunks that cp.async
 // lays down (16-byte pieces XOR-swizzled by row & 7, 1024-byte 8-row groups) ARE the K-major SWIZZLE_128B
@@ -999,10 +1262,11 @@ static_assert(TT_DATA_BYTES >= 2 * NB * 132 * 4, "output staging must fit");
 enum { TT_BAR_WORK = 6, TT_BAR_FULL0 = 7 };          // named barriers 7, 8, 9: stage s handed to the MMA warp
 constexpr int TT_DRAIN = 8;                          // chunks per TMEM accumulation chain (256 columns)
 static_assert(TT_STAGES * TT_STAGE_BYTES >= FI_SMEM_FLOATS * 4, "potf2 scratch must fit in the pipeline buffers");
+static_assert(TT_STAGES * TT_STAGE_BYTES >= FS_SMEM_FLOATS * 4, "split potf2 scratch must fit in the pipeline buffers");
 
 __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
   extern __shared__ uint8_t tsm_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsm_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm = smem_align1024(tsm_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TT_DATA_BYTES);
   uint64_t* mma_done = bars;          // [TT_STAGES]
   uint64_t* acc_done = bars + TT_STAGES;
@@ -1219,7 +1483,7 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
       float* Tt = fsm;
       float* Ww = Tt + FI_T_FLOATS;
       float* Pn = Ww + FI_T_FLOATS;
-      float* Wp = Pn + 2 * 8 * NB;
+      float* Wp = Pn + (g.fi_nt > 0 ? FS_PN_FLOATS : 2 * 8 * NB);
       float* Dd = Wp + 2 * 8 * NB;
       {
         const int tir = R >> 2;
@@ -1238,8 +1502,12 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
       }
       __syncthreads();
       bool bad = false;
-      factor_invert_la(Tt, Ww, Pn, Wp, Dd, bad, tid,
-                       (g.trace != nullptr && c == 1) ? reinterpret_cast<long long*>(g.trace + (int64_t)g.ntasks * 8) : nullptr);
+      if (g.fi_nt > 0)
+        factor_invert_split(Tt, Ww, Pn, Wp, Dd, reinterpret_cast<int*>(Dd + 16 * 64), bad, tid, g.fi_nt,
+                            (g.trace != nullptr && c == 1) ? reinterpret_cast<long long*>(g.trace + (int64_t)g.ntasks * 8) : nullptr);
+      else
+        factor_invert_la(Tt, Ww, Pn, Wp, Dd, bad, tid,
+                         (g.trace != nullptr && c == 1) ? reinterpret_cast<long long*>(g.trace + (int64_t)g.ntasks * 8) : nullptr);
       if (bad && g.status) atomicOr(g.status, LCB_ST_NOT_SPD);
       if (tr) tr[4] = gtime_ns();
       {  // Linv(c) -> dinv[c] hi / lo (row-major), a warp per row: coalesced 512-byte stores
@@ -1536,6 +1804,14 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
     ta.flagL = flags; ta.flagY = flags + nblk * nblk; ta.counter = flags + 2 * nblk * nblk;
     ta.status = status; ta.ld = k; ta.k = (int)k; ta.nblk = (int)nblk; ta.c0 = 0; ta.c1 = (int)nblk; ta.with_inv = 1;
     ta.ntasks = (int)(nblk * nblk);
+    {  // LCB_CHOL_FI=0: joint-worker potf2 (round-2 first form); 1..6: T-worker warps of the split form (default 4)
+      static int fi = -1;
+      if (fi < 0) {
+        const char* e = getenv("LCB_CHOL_FI");
+        fi = (e && e[0] >= '0' && e[0] <= '6') ? (e[0] - '0') : 4;
+      }
+      ta.fi_nt = fi;
+    }
     if (getenv("LCB_CHOL_TRACE")) {  // debug: task trace at byte offset lcb_chol_trace_offset(k) of the workspace
       ta.trace = reinterpret_cast<unsigned long long*>(w0 + tiles_trace_offset(k));
       LCB_CUDA(cudaMemsetAsync(ta.trace, 0, ((size_t)ta.ntasks * 16 + TILES_TRACE_EXTRA) * sizeof(float), st));

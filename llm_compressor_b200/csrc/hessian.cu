@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 hessian_umma_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant__ XMaps maps_b,
                     const __grid_constant__ CUtensorMap map_h, const __grid_constant__ HessArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* smem_out = smem + STAGES * STAGE_BYTES;  // 1024-aligned: [warp 0..3][buf 0..1][4096]
@@ -324,7 +324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 hessian_umma_pair_kernel(const __grid_constant__ XMaps maps_a, const __grid_constant__ XMaps maps_b,
                          const __grid_constant__ CUtensorMap map_h, const __grid_constant__ HessArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + P_STAGES * PA_BYTES;
   uint8_t* smem_out = smem + P_STAGES * P_STAGE_BYTES;

@@ -56,7 +56,7 @@ template <bool QUANT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ QgArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;                    // TMA landed
   uint64_t* ready = bars + STAGES;          // transformed (QUANT) -- what the MMA warp waits on

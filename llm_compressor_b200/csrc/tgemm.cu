@@ -74,7 +74,7 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
                 const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ TgArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* smem_out = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + OUT_BYTES);
   uint64_t* full = bars;

@@ -10,6 +10,12 @@
 namespace lcb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 1024-byte aligned start of a dynamic shared-memory array (SWIZZLE_128B atoms).  Pointer arithmetic on the array, NOT an
+// integer round trip: `(T*)((uintptr_t(raw) + 1023) & ~1023)` loses the address space and every access through the
+// result compiles to a generic LD.E / ST.E (64-bit address math, slower path) instead of LDS / STS.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

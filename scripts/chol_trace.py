@@ -48,6 +48,7 @@ if ys:
 # per-step clock64 probes inside factor_invert_la of diagonal task c = 1 (cycles, relative to step 0 start)
 dbg = ws[off + nblk * nblk * 64: off + nblk * nblk * 64 + 16 * 12 * 8].cpu().numpy().view(np.int64).reshape(16, 12)
 b0 = dbg[0, 0]
-print("step: chain[P1start P1end P3Async LAend] worker0[P1sync P2Wend LAsync first P3end barW]  (cycles since step-0 start)")
+print("joint form (LCB_CHOL_FI=0): chain[P1start P1end P3Async LAend] worker0[P1sync P2Wend LAsync first P3end barW]")
+print("split form: chain[start factored P3Async LAend] Tworker0[P1sync solved LAsync first trailing_end] Wworker0[start end]  (cycles since step-0 start)")
 for p in range(16):
-    print("  p=%2d " % p + " ".join("%7d" % (int(v - b0) if v else -1) for v in dbg[p, :10]))
+    print("  p=%2d " % p + " ".join("%7d" % (int(v - b0) if v else -1) for v in dbg[p, :11]))
