@@ -184,27 +184,49 @@ def fused_qlinear_times(lc, torch, dev):
 
 def rotation_bandwidth(torch, dev, hbm_gbs):
     """randomised Hadamard rotation W @ R1 (lcb_hadamard_rows) on a [65536, n] bf16 tensor (larger than
-    L2), n = 3072 (Llama-3.2-3B hidden, K = 12) and 2560 (Gemma-3 / Qwen3 hidden, K = 40).  4 B / element (read + write)."""
+    L2), n = 3072 (Llama-3.2-3B hidden, K = 12), 2560 (Gemma-3 / Qwen3 hidden, K = 40), 8192 (Llama-3.2-3B FFN).
+    4 B / element (read + write).  Beside it the reference's vendored third-party FWHT (oracle/_ref, built unmodified for
+    sm_100a by oracle/make_fht.py) on the same tensor: no sign vector there, so its time is a lower bound for the
+    reference's rotation."""
     from llm_compressor_b200 import hadamard as H
+    F = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+        import fast_hadamard_transform_cuda as F
+    except Exception:
+        F = None
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 10
+
     out = {}
-    for n in (3072, 2560):
+    for n in (3072, 2560, 8192):
         g = torch.Generator(device=dev).manual_seed(n)
         x = (0.02 * torch.randn(8 * 8192, n, generator=g, device=dev)).to(torch.bfloat16)
         s = (torch.randint(0, 2, (n,), generator=g, device=dev) * 2 - 1).float()
         y = torch.empty_like(x)
         for acc64 in (True, False):
-            for _ in range(3):
-                H.hadamard_rows(x, s, acc64=acc64, out=y)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(10):
-                H.hadamard_rows(x, s, acc64=acc64, out=y)
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / 10
+            ms = timed(lambda: H.hadamard_rows(x, s, acc64=acc64, out=y))
             gbs = x.numel() * 4 / ms / 1e6
             out["n%d_%s" % (n, "fp64acc" if acc64 else "fp32acc")] = {"GBs": gbs, "frac_of_hbm_peak": gbs / hbm_gbs, "ms": ms}
+        if F is not None:
+            K = next(k for k in (1, 12, 20, 28, 40) if n % k == 0 and ((n // k) & (n // k - 1)) == 0)
+            fn = {1: F.fast_hadamard_transform, 12: F.fast_hadamard_transform_12N, 20: F.fast_hadamard_transform_20N,
+                  28: F.fast_hadamard_transform_28N, 40: F.fast_hadamard_transform_40N}[K]
+            try:
+                ms = timed(lambda: fn(x, 1.0 / n ** 0.5))
+                out["n%d_third_party_fwht" % n] = {"GBs": x.numel() * 4 / ms / 1e6, "ms": ms}
+            except Exception as e:
+                out["n%d_third_party_fwht" % n] = {"unavailable": str(e)[:80]}
         del x, y
     return out
 

@@ -14,6 +14,7 @@
 //   * accumulation in fp64 (default: results round to the same bf16 / fp32 values as the reference's fp64 GEMM
 //     up to ~1e-16 relative) or fp32.
 #include <algorithm>
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -568,6 +569,315 @@ int launch_tile_k(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Register kernel (bf16 in, fp32 accumulation, the row widths of the model zoo).  The tiled kernel above moves every
+// element through shared memory once per pass (24 B / element for n = 3072): at 2.7 TB/s of HBM traffic the shared-memory
+// pipe is half busy and the barrier-separated passes cannot hide it.  Here a row is held in the REGISTERS of TPR = 32 or 64
+// threads and crosses shared memory exactly twice (8 B as fp32 between the two register phases, 2 x the output size on
+// the way out):
+//   element i = j (n / V) + 8 t + e      j < V = KT 2^X   vector index of thread t (the H_K index and the top X bits)
+//                                        t < TPR = 2^LT   thread of the row group
+//                                        e < 8            position inside the 16-byte vector
+//   phase A  thread t loads its V vectors (16-byte loads, a warp reads 512 contiguous bytes per j), flips the signs, and
+//            runs H_K and the radix-2 stages of the X + 3 register-resident bits on its EPT = 8 V values;
+//   A -> B   S[t][c] (fp32, row stride EPT + 4: 128-bit stores, conflict-free), thread u reads back the CB = EPT / TPR
+//            values c in [u CB, (u + 1) CB) of EVERY t;
+//   phase B  the LT stages across t, scaling, conversion;
+//   B -> C   output row image O[j][t][e] (8 elements of padding per j: conflict-free scalar stores), read back as 16-byte
+//            vectors in the layout of phase A and stored with the access pattern of the loads.
+// A group of TPR threads owns a row from load to store: groups only synchronise internally (__syncwarp for TPR = 32, a
+// 64-thread named barrier for TPR = 64), never the CTA.
+// A shape: EV elements per vector (8 = 16-byte loads, 4 = 8-byte loads), V vectors per thread, TPR = 2^LT threads per row.
+//   STRIDED == false: phase-B thread u owns the CB = EPT / TPR columns [u CB, (u + 1) CB)           (EPT % TPR == 0)
+//   STRIDED == true : phase-B thread u owns the columns u, u + TPR, ... < EPT (NK = ceil(EPT / TPR) rounds, the last ragged)
+template <int KT_, int X, int LT_, int EV_ = 8, bool STRIDED_ = false>
+struct RegShape {
+  static constexpr int KT = KT_, LT = LT_, EV = EV_;
+  static constexpr bool STRIDED = STRIDED_;
+  // KT == 40: H_40 = H_2 (x) H_20; the 20 values of H_20 are a thread's vectors, the H_2 bit joins the thread index
+  static constexpr int KB = KT == 40 ? 20 : KT;
+  static constexpr int V = KB << X, EPT = EV * V, TPR = 1 << LT, N = EPT * TPR, SA = EPT + 4;
+  static constexpr int NK = (EPT + TPR - 1) / TPR;      // columns per phase-B thread (rounded up when STRIDED)
+  static constexpr int OJ = TPR * EV + 8;               // elements per j of the output image
+  static constexpr int GROUP_BYTES = TPR * SA * 4 > V * OJ * 4 ? TPR * SA * 4 : V * OJ * 4;   // S and the output image share it
+  static_assert(STRIDED || EPT % TPR == 0, "blocked columns: every phase-B thread holds whole columns");
+  static_assert(KT == 1 || X == 0, "H_K needs all K values of a column in one thread");
+  static_assert(LT >= 3 && LT <= 6, "row groups of 8 .. 64 threads");
+  static_assert(KT != 40 || (LT == 5 && EV == 4) || (LT == 4 && EV == 8), "K = 40: n = 2560, thread = (H_2 bit, upper bits of b)");
+  // position (in vectors of EV elements) of vector j of thread t inside the row
+  __device__ static __forceinline__ int vec(int j, int t) {
+    if constexpr (KT == 40) return (t >> (LT - 1)) * (20 << (LT - 1)) + (j << (LT - 1)) + (t & ((1 << (LT - 1)) - 1));
+    else return j * TPR + t;
+  }
+  // column of phase-B thread u, round k
+  __device__ static __forceinline__ int col(int u, int k) { return STRIDED ? u + TPR * k : u * NK + k; }
+};
+
+// Packed fp32 pairs (sm_100 add / sub / mul .f32x2 -> FADD2 / FMUL2): one instruction for two lanes' worth of adds.  The
+// kernel is bound by instruction issue (13 adds per element for n = 3072), so every stage whose two operands are
+// neighbours in the register array runs on pairs.
+struct F2 {
+  uint64_t v;
+  __device__ __forceinline__ F2() {}
+  __device__ __forceinline__ F2(int) : v(0ull) {}   // zero (the accumulator start of paley_dot)
+  __device__ __forceinline__ F2(float lo, float hi) { asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); }
+  __device__ __forceinline__ void unpack(float& lo, float& hi) const { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+  friend __device__ __forceinline__ F2 operator+(F2 a, F2 b) {
+    F2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+  }
+  friend __device__ __forceinline__ F2 operator-(F2 a, F2 b) {
+    F2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+  }
+  friend __device__ __forceinline__ F2 operator*(F2 a, F2 b) {
+    F2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+  }
+  __device__ __forceinline__ F2 operator-() const { return F2(0) - *this; }
+};
+
+template <int KB, int... Rs>
+__device__ __forceinline__ void paley_out(const F2 (&v)[KB], F2 (&o)[KB], std::integer_sequence<int, Rs...>) {
+  F2 cmb[KB / 4][8];
+  paley_groups<F2, KB>(v, cmb);
+  ((o[Rs] = paley_dot<F2, KB, Rs>(cmb)), ...);
+}
+
+template <int N, int H0, int H1>  // radix-2 stages with strides H0, 2 H0, ... < H1 over a register array (N even)
+__device__ __forceinline__ void bfly_range(float (&v)[N]) {
+#pragma unroll
+  for (int h = H0; h < H1; h <<= 1) {
+    if (h == 1) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        const float p = v[j], q = v[j + 1];
+        v[j] = p + q;
+        v[j + 1] = p - q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        if ((j & h) == 0) {
+          const F2 p(v[j], v[j + 1]), q(v[j | h], v[(j | h) + 1]);
+          (p + q).unpack(v[j], v[j + 1]);
+          (p - q).unpack(v[j | h], v[(j | h) + 1]);
+        }
+      }
+    }
+  }
+}
+
+template <int LT>
+__device__ __forceinline__ void group_sync(int grp) {
+  if constexpr (LT == 5) __syncwarp();
+  else if constexpr (LT < 5)   // several row groups per warp, independent trip counts: only this group's lanes
+    __syncwarp((LT == 4 ? 0xffffu : 0xffu) << ((1 << LT) * (grp & ((32 >> LT) - 1))));
+  else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(1 << LT) : "memory");
+}
+
+template <typename TOut, typename S, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) hadamard_reg_kernel(const __grid_constant__ HadArgs a) {
+  constexpr int KT = S::KT, LT = S::LT, EV = S::EV, V = S::V, EPT = S::EPT, TPR = S::TPR, N = S::N, NK = S::NK, SA = S::SA, OJ = S::OJ;
+  constexpr int GROUPS = THREADS >> LT;
+  constexpr int WPV = EV / 2;   // 32-bit words per vector
+  extern __shared__ __align__(16) unsigned char had_smem[];
+  uint32_t* sgn = reinterpret_cast<uint32_t*>(had_smem);   // [N / 2] XOR masks, two elements per word, row order
+  const int tid = threadIdx.x, grp = tid >> LT, t = tid & (TPR - 1);
+  float* Sg = reinterpret_cast<float*>(had_smem + N * 2 + grp * S::GROUP_BYTES);
+  TOut* Og = reinterpret_cast<TOut*>(Sg);
+  const bool flip = a.signs != nullptr;
+  if (flip) {
+    for (int i = tid; i < N / 2; i += THREADS)
+      sgn[i] = (a.signs[2 * i] < 0.0f ? 0x8000u : 0u) | (a.signs[2 * i + 1] < 0.0f ? 0x80000000u : 0u);
+  }
+  __syncthreads();
+  const float rcp = (float)a.rcp;
+  int oofs[NK];      // where this thread's columns go in the output image
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int c = S::col(t, k);
+    oofs[k] = (c / EV) * OJ + (c % EV);
+  }
+  const uint32_t* xin = static_cast<const uint32_t*>(a.x);
+  for (int64_t row = (int64_t)blockIdx.x * GROUPS + grp; row < a.rows; row += (int64_t)gridDim.x * GROUPS) {
+    float r[EPT];
+    {  // ---- phase A: load, sign flip, unpack
+      const uint32_t* src = xin + row * (int64_t)(N / 2);
+      uint32_t raw[V][WPV];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        if constexpr (EV == 8) {
+          const uint4 w = __ldcs(reinterpret_cast<const uint4*>(src) + S::vec(j, t));
+          raw[j][0] = w.x; raw[j][1] = w.y; raw[j][2] = w.z; raw[j][3] = w.w;
+        } else {
+          const uint2 w = __ldcs(reinterpret_cast<const uint2*>(src) + S::vec(j, t));
+          raw[j][0] = w.x; raw[j][1] = w.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        uint32_t mk[WPV];
+        if (flip) {
+          if constexpr (EV == 8) {
+            const uint4 m4 = reinterpret_cast<const uint4*>(sgn)[S::vec(j, t)];
+            mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+          } else {
+            const uint2 m2 = reinterpret_cast<const uint2*>(sgn)[S::vec(j, t)];
+            mk[0] = m2.x; mk[1] = m2.y;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < WPV; ++q) {
+          const uint32_t w = flip ? (raw[j][q] ^ mk[q]) : raw[j][q];
+          r[EV * j + 2 * q] = __uint_as_float(w << 16);
+          r[EV * j + 2 * q + 1] = __uint_as_float(w & 0xffff0000u);
+        }
+      }
+    }
+    if constexpr (KT == 1) {
+      bfly_range<EPT, 1, EPT>(r);
+    } else {
+      bfly_range<EPT, 1, EV>(r);
+      static_assert(KT == 1 || KT == 12 || KT == 40, "register kernel: H_12 and H_40 = H_2 (x) H_20 only");
+      constexpr int KB = S::KB;
+#pragma unroll
+      for (int e = 0; e < EV; e += 2) {   // two neighbouring columns per packed H_K
+        F2 v[KB], o[KB];
+#pragma unroll
+        for (int c = 0; c < KB; ++c) v[c] = F2(r[EV * c + e], r[EV * c + e + 1]);
+        paley_out<KB>(v, o, std::make_integer_sequence<int, KB>{});
+#pragma unroll
+        for (int c = 0; c < KB; ++c) o[c].unpack(r[EV * c + e], r[EV * c + e + 1]);
+      }
+    }
+    // ---- A -> B
+#pragma unroll
+    for (int q = 0; q < EPT / 4; ++q)
+      *reinterpret_cast<float4*>(Sg + t * SA + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    group_sync<LT>(grp);
+    float vb[NK][TPR];
+#pragma unroll
+    for (int tt = 0; tt < TPR; ++tt) {
+      if constexpr (S::STRIDED) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+          if ((k + 1) * TPR <= EPT || t + TPR * k < EPT) vb[k][tt] = Sg[tt * SA + t + TPR * k];
+      } else {
+        const float* p = Sg + tt * SA + t * NK;
+        if constexpr (NK % 4 == 0) {
+#pragma unroll
+          for (int k = 0; k < NK; k += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(p + k);
+            vb[k][tt] = f.x; vb[k + 1][tt] = f.y; vb[k + 2][tt] = f.z; vb[k + 3][tt] = f.w;
+          }
+        } else if constexpr (NK % 2 == 0) {
+#pragma unroll
+          for (int k = 0; k < NK; k += 2) {
+            const float2 f = *reinterpret_cast<const float2*>(p + k);
+            vb[k][tt] = f.x; vb[k + 1][tt] = f.y;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NK; ++k) vb[k][tt] = p[k];
+        }
+      }
+    }
+    group_sync<LT>(grp);   // every read of S is done: the output image may overwrite it
+    // ---- phase B + B -> C
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      if ((k + 1) * TPR <= EPT || !S::STRIDED || t + TPR * k < EPT) {
+        bfly_range<TPR, 1, TPR>(vb[k]);
+        TOut* o = Og + oofs[k];
+        const F2 rcp2(rcp, rcp);
+#pragma unroll
+        for (int tt = 0; tt < TPR; tt += 2) {
+          float y0, y1;
+          (F2(vb[k][tt], vb[k][tt + 1]) * rcp2).unpack(y0, y1);
+          if constexpr (sizeof(TOut) == 2) {
+            o[tt * EV] = __float2bfloat16_rn(y0);
+            o[(tt + 1) * EV] = __float2bfloat16_rn(y1);
+          } else {
+            o[tt * EV] = y0;
+            o[(tt + 1) * EV] = y1;
+          }
+        }
+      }
+    }
+    group_sync<LT>(grp);
+    {
+      constexpr int OB = EV * (int)sizeof(TOut);   // bytes per output vector: 8, 16 or 32
+      unsigned char* dst = static_cast<unsigned char*>(a.y) + row * (int64_t)N * (int64_t)sizeof(TOut);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(Og + j * OJ + t * EV);
+        unsigned char* d = dst + (int64_t)S::vec(j, t) * OB;
+        if constexpr (OB == 8) {
+          __stcs(reinterpret_cast<uint2*>(d), *reinterpret_cast<const uint2*>(p));
+        } else {
+#pragma unroll
+          for (int q = 0; q < OB / 16; ++q) __stcs(reinterpret_cast<uint4*>(d) + q, reinterpret_cast<const uint4*>(p)[q]);
+        }
+      }
+    }
+    group_sync<LT>(grp);   // the image is read: the next row may overwrite S
+  }
+}
+
+template <typename TOut, typename S, int THREADS, int MINB>
+int launch_reg(const HadArgs& a, cudaStream_t st) {
+  constexpr int GROUPS = THREADS >> S::LT;
+  const size_t smem = (size_t)S::N * 2 + (size_t)GROUPS * S::GROUP_BYTES;
+  auto kern = hadamard_reg_kernel<TOut, S, THREADS, MINB>;
+  LCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(MINB, (227 * 1024) / (smem + 1024)));
+  const int grid = (int)std::min<int64_t>(ceil_div(a.rows, GROUPS), (int64_t)sm_count() * per_sm);
+  kern<<<grid, THREADS, smem, st>>>(a);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+// n -> register-kernel configuration; returns -1 when the width has none
+template <typename TOut>
+int launch_reg_n(const HadArgs& a, cudaStream_t st) {
+  static int var = -1;   // LCB_HAD_VAR=1: alternative configurations (A/B runs)
+  if (var < 0) {
+    const char* e = getenv("LCB_HAD_VAR");
+    var = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (a.K == 12 && a.m == 8) return launch_reg<TOut, RegShape<12, 0, 5>, 128, 3>(a, st);   // 3072
+  if (a.K == 40 && a.m == 6)                                                                // 2560
+    return var ? launch_reg<TOut, RegShape<40, 0, 4>, 128, 2>(a, st) : launch_reg<TOut, RegShape<40, 0, 5, 4, true>, 128, 3>(a, st);
+  if (a.K == 1) {
+    switch (a.m) {
+      case 6: return launch_reg<TOut, RegShape<1, 0, 3>, 256, 4>(a, st);    // 64   (head dims: 8 threads per row)
+      case 7: return launch_reg<TOut, RegShape<1, 1, 3>, 256, 4>(a, st);    // 128
+      case 8: return launch_reg<TOut, RegShape<1, 1, 4>, 256, 4>(a, st);    // 256
+      case 9: return launch_reg<TOut, RegShape<1, 2, 4>, 256, 4>(a, st);    // 512
+      case 10: return launch_reg<TOut, RegShape<1, 2, 5>, 256, 4>(a, st);   // 1024
+      case 11: return launch_reg<TOut, RegShape<1, 3, 5>, 256, 2>(a, st);   // 2048
+      case 12: return launch_reg<TOut, RegShape<1, 3, 6>, 256, 2>(a, st);   // 4096
+      case 13:                                                              // 8192: 6 rows in flight per SM (a row's S is 33 KB)
+        return var ? launch_reg<TOut, RegShape<1, 4, 6>, 128, 2>(a, st) : launch_reg<TOut, RegShape<1, 4, 6>, 384, 1>(a, st);
+      default: break;
+    }
+  }
+  return -1;
+}
+
+static int reg_mode() {   // LCB_HAD_REG=0: tiled kernel for every shape (A/B runs)
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("LCB_HAD_REG");
+    m = (e && e[0] == '0') ? 0 : 1;
+  }
+  return m;
+}
+
 template <typename Acc, int KT>
 int launch_had(const HadArgs& a, int grid, size_t smem, cudaStream_t st) {
   LCB_CUDA(cudaFuncSetAttribute(hadamard_rows_kernel<Acc, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -626,6 +936,12 @@ extern "C" int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t esz_in = dtype_in == LCB_BF16 ? 2 : (dtype_in == LCB_F32 ? 4 : 8);
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (!acc64 && aligned && dtype_in == LCB_BF16 && dtype_out != LCB_F64 && (K == 1 || K == 12 || K == 40) && reg_mode() != 0 &&
+      !transpose_table(hadk_bits, K)) {
+    // register kernel: bf16 rows of the common widths, fp32 accumulation
+    const int rc = dtype_out == LCB_BF16 ? launch_reg_n<__nv_bfloat16>(a, st) : launch_reg_n<float>(a, st);
+    if (rc >= 0) return rc;
+  }
   if (m >= 5 && aligned && dtype_in != LCB_F64 && (K == 1 || K == 12 || K == 40) && !transpose_table(hadk_bits, K)) {
     // tiled kernel: raw tile + padded work buffer + sign words; aim at two resident CTAs per SM
     const int64_t budget = 100 * 1024;

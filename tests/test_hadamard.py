@@ -99,6 +99,34 @@ def test_cuda_rotation_vs_oracle_and_dense_gemm(rows, n, dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rows,n", [(37, 1024), (300, 2048), (257, 3072), (1030, 3072), (131, 4096), (67, 8192), (600, 8192), (45, 2560), (777, 2560), (1000, 128), (77, 64), (50, 256), (33, 512)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("with_signs", [True, False])
+def test_register_kernel_fp32_accumulation(rows, n, out_dtype, with_signs):
+    """The register-resident kernel (bf16 rows of the common widths, acc64=False; hadamard.cu hadamard_reg_kernel):
+    every output within fp32 accumulation error of the exact transform (2e-6 of the row scale for fp32 output, one bf16
+    rounding for bf16 output), ragged row counts, in place, and nearly everywhere the same bf16 value as the fp64 path."""
+    from llm_compressor_b200 import hadamard as H
+    g = torch.Generator().manual_seed(rows * 7 + n)
+    W = (0.02 * torch.randn(rows, n, generator=g) * torch.exp(torch.randn(rows, 1, generator=g))).to(torch.bfloat16)
+    s = (torch.randint(0, 2, (n,), generator=g) * 2 - 1).double() if with_signs else None
+    exact = orc.matmul_hadU(W.double().numpy(), signs=None if s is None else s.numpy())
+    sd = None if s is None else s.to(DEV)
+    got = H.hadamard_rows(W.to(DEV), sd, out_dtype=out_dtype, acc64=False)
+    assert got.dtype == out_dtype
+    err = np.abs(got.double().cpu().numpy() - exact)
+    scale = np.abs(exact).max(axis=1, keepdims=True) + 1e-30
+    tol = 2e-6 if out_dtype == torch.float32 else 2.0 ** -8
+    assert float((err / scale).max()) <= tol, float((err / scale).max())
+    if out_dtype == torch.bfloat16:
+        ref64 = H.hadamard_rows(W.to(DEV), sd, acc64=True)
+        assert float((got != ref64).float().mean()) < 1e-3      # fp32 sums differ from fp64 sums only at rounding ties
+        z = W.to(DEV).clone()
+        H.hadamard_rows(z, sd, acc64=False, out=z)              # in place
+        assert torch.equal(z, got)
+
+
+@pytest.mark.gpu
 def test_transform_is_orthogonal_and_in_place_at_full_size():
     from llm_compressor_b200 import hadamard as H
     for n in (2560, 3072, 8192):
