@@ -278,7 +278,8 @@ int lcb_apply_mask(void* W, int dtype, const uint8_t* mask, int64_t numel, void*
  * apply_exact_had_to_linear).  For every row of x [rows, n] (contiguous):
  *     y = T(signs .* x) / divisor,   T = (H_K (x) I_L)(I_K (x) H_L),  n = K * L,  L = 2^m
  * i.e. x @ (diag(signs) * matmul_hadU(I)) computed as a fast Walsh-Hadamard transform instead of the reference's
- * dense fp64 GEMM.  hadk_bits: HOST array of K words, bit a of word a' set <=> H_K[a'][a] == -1 (K == 1: null);
+ * dense fp64 GEMM.  hadk_bits: HOST array; K <= 64: K words, bit a of word a' set <=> H_K[a'][a] == -1 (K == 1: null);
+ * 64 < K <= 172 (the had108 .. had172 blocks): 3 words per row, bit (a & 63) of word 3 a' + (a >> 6);
  * signs: device [n] of +-1 or null; divisor: float32(sqrt(n)) for the reference's normalisation;
  * acc64 != 0 accumulates in fp64 (reference precision), else fp32.  x / y dtypes: LCB_F32 / LCB_BF16 / LCB_F64;
  * in place (x == y) is allowed.  Column transforms (R^T @ W) are row transforms of the transpose. */

@@ -193,6 +193,71 @@ __global__ void __launch_bounds__(HAD_THREADS) hadamard_rows_kernel(const __grid
 }
 
 
+// K > 64 (the reference's had108 / had140 / had156 / had172 blocks: Llama-1 / Llama-2 intermediate sizes such as
+// 11008 = 172 * 64): the sign table no longer fits one 64-bit word per row; it travels as HAD_BIGW words per row in a larger
+// parameter block of its own kernel, so that the launches of the common shapes keep their small parameter block.
+constexpr int HAD_BIGK = 172;
+constexpr int HAD_BIGW = 3;
+struct HadArgsBig {
+  HadArgs b;
+  unsigned long long hkx[HAD_BIGK * HAD_BIGW];  // bit (a & 63) of hkx[a' * HAD_BIGW + (a >> 6)] set  <=>  H_K[a'][a] == -1
+};
+
+template <typename Acc>
+__global__ void __launch_bounds__(HAD_THREADS) hadamard_rows_bigk_kernel(const __grid_constant__ HadArgsBig ab) {
+  extern __shared__ __align__(16) unsigned char had_smem[];
+  Acc* sm = reinterpret_cast<Acc*>(had_smem);
+  const HadArgs& a = ab.b;
+  const int r0 = a.m < 4 ? a.m : 4;
+  const int L = 1 << a.m;
+  for (int64_t row0 = (int64_t)blockIdx.x * a.rpc; row0 < a.rows; row0 += (int64_t)gridDim.x * a.rpc) {
+    const int nr = (int)min((int64_t)a.rpc, a.rows - row0);
+    switch (r0) {
+      case 4: first_pass<Acc, 4>(a, sm, row0, nr, false); break;
+      case 3: first_pass<Acc, 3>(a, sm, row0, nr, false); break;
+      case 2: first_pass<Acc, 2>(a, sm, row0, nr, false); break;
+      case 1: first_pass<Acc, 1>(a, sm, row0, nr, false); break;
+      default: first_pass<Acc, 0>(a, sm, row0, nr, false); break;
+    }
+    __syncthreads();
+    for (int done = r0; done < a.m;) {
+      const int r = (a.m - done) < 4 ? (a.m - done) : 4;
+      switch (r) {
+        case 4: mid_pass<Acc, 4>(a, sm, row0, nr, done, false); break;
+        case 3: mid_pass<Acc, 3>(a, sm, row0, nr, done, false); break;
+        case 2: mid_pass<Acc, 2>(a, sm, row0, nr, done, false); break;
+        default: mid_pass<Acc, 1>(a, sm, row0, nr, done, false); break;
+      }
+      __syncthreads();
+      done += r;
+    }
+    // y[a', b] = sum_a H_K[a'][a] v[a, b]
+    for (int q = threadIdx.x; q < nr * L; q += HAD_THREADS) {
+      const int row = q >> a.m, b = q & (L - 1);
+      const int sbase = row * a.n + b;
+      const int64_t gbase = (row0 + row) * (int64_t)a.n + b;
+      for (int r = 0; r < a.K; ++r) {
+        const unsigned long long* bits = ab.hkx + r * HAD_BIGW;
+        Acc acc = 0;
+        for (int c = 0; c < a.K; ++c) {
+          const Acc t = sm[pad(sbase + (c << a.m))];
+          acc += ((bits[c >> 6] >> (c & 63)) & 1ull) ? -t : t;
+        }
+        store_out<Acc>(a.y, a.dt_out, gbase + ((int64_t)r << a.m), acc / (Acc)a.divisor);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename Acc>
+int launch_had_big(const HadArgsBig& ab, int grid, size_t smem, cudaStream_t st) {
+  LCB_CUDA(cudaFuncSetAttribute(hadamard_rows_bigk_kernel<Acc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hadamard_rows_bigk_kernel<Acc><<<grid, HAD_THREADS, smem, st>>>(ab);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Tiled kernel (m >= 5, bf16 / fp32 input, K in {1, 12, 40}): all global traffic is 16-byte vectors and the inner
 // loops are (nearly) one instruction per add.  The tile (rpc whole rows, one contiguous chunk) is copied raw into
@@ -849,7 +914,7 @@ int launch_reg_n(const HadArgs& a, cudaStream_t st) {
     const char* e = getenv("LCB_HAD_VAR");
     var = (e && e[0] == '1') ? 1 : 0;
   }
-  if (a.K == 12 && a.m == 8) return launch_reg<TOut, RegShape<12, 0, 5>, 128, 3>(a, st);   // 3072
+  if (a.K == 12 && a.m == 8) return launch_reg<TOut, RegShape<12, 0, 5>, 128, 3>(a, st);   // 3072 (64 threads x 48 values per row: 3.4 TB/s)
   if (a.K == 40 && a.m == 6)                                                                // 2560
     return var ? launch_reg<TOut, RegShape<40, 0, 4>, 128, 2>(a, st) : launch_reg<TOut, RegShape<40, 0, 5, 4, true>, 128, 3>(a, st);
   if (a.K == 1) {
@@ -918,7 +983,7 @@ static bool transpose_table(const uint64_t* bits, int K) {
 extern "C" int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype_out, int64_t rows, int64_t n,
                                  const float* signs, const uint64_t* hadk_bits, int K, double divisor, int acc64,
                                  void* stream) {
-  LCB_REQUIRE(x && y && rows >= 0 && n > 0 && K >= 1 && K <= HAD_MAXK && divisor != 0.0, "lcb_hadamard_rows: bad arguments");
+  LCB_REQUIRE(x && y && rows >= 0 && n > 0 && K >= 1 && K <= HAD_BIGK && divisor != 0.0, "lcb_hadamard_rows: bad arguments");
   LCB_REQUIRE(dtype_in >= LCB_F32 && dtype_in <= LCB_F64 && dtype_out >= LCB_F32 && dtype_out <= LCB_F64,
               "lcb_hadamard_rows: dtype must be LCB_F32, LCB_BF16 or LCB_F64");
   LCB_REQUIRE(K == 1 || hadk_bits != nullptr, "lcb_hadamard_rows: K > 1 needs the H_K sign table");
@@ -932,7 +997,7 @@ extern "C" int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype
   HadArgs a{};
   a.x = x; a.y = y; a.signs = signs; a.rows = rows; a.n = (int)n; a.m = m; a.K = K;
   a.dt_in = dtype_in; a.dt_out = dtype_out; a.divisor = divisor; a.rcp = 1.0 / divisor;
-  for (int i = 0; i < K && K > 1; ++i) a.hk[i] = hadk_bits[i];
+  for (int i = 0; i < K && K > 1 && K <= HAD_MAXK; ++i) a.hk[i] = hadk_bits[i];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t esz_in = dtype_in == LCB_BF16 ? 2 : (dtype_in == LCB_F32 ? 4 : 8);
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
@@ -976,5 +1041,11 @@ extern "C" int lcb_hadamard_rows(const void* x, int dtype_in, void* y, int dtype
   const int64_t tiles = ceil_div(rows, a.rpc);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * per_sm);
+  if (K > HAD_MAXK) {   // HAD_BIGW words per row
+    HadArgsBig ab{};
+    ab.b = a;
+    for (int i = 0; i < K * HAD_BIGW; ++i) ab.hkx[i] = hadk_bits[i];
+    return acc64 ? launch_had_big<double>(ab, grid, smem, st) : launch_had_big<float>(ab, grid, smem, st);
+  }
   return acc64 ? launch_had_k<double>(a, grid, smem, st) : launch_had_k<float>(a, grid, smem, st);
 }

@@ -12,8 +12,11 @@ are NOT Hadamard-structured (random orthogonal / trained R.bin matrices) take th
 The fixed H_K blocks are generated, not tabulated: the reference's had12 / had20 / had44 / had60 are Paley-I
 matrices [[1, -1^T], [1, I - Q^T]] (Q the Jacobsthal matrix of GF(q), q = K - 1), had28 / had36 are Paley-II
 [[S+I, S-I], [S-I, -S-I]] (S the symmetric conference matrix of order K/2) and had40 is the Sylvester double of
-had20 -- checked entry by entry against the reference's tables by tests/test_oracle_golden.py.  The Williamson /
-other tables (52, 108, 140, 156, 172: Llama-1/2 13B-70B widths) are not generated; get_hadK raises for them.
+had20; had108 / had140 (Llama-1 13B / 30B intermediate sizes) are Paley-I again (q = 107, 139); had52 / had156 / had172
+(Llama-1 13B hidden, 30B 3x hidden, Llama-2 7B+ intermediate 11008 = 172 * 64) are Williamson matrices
+[[A, B, C, D], [-B, A, -D, C], [-C, D, A, -B], [-D, -C, B, A]] of four symmetric circulants whose first rows are the
+classical Williamson sequences of order 13 / 39 / 43 (`_WILLIAMSON`) -- all checked entry by entry against the
+reference's tables by tests/test_hadamard.py.
 """
 import ctypes
 import functools
@@ -60,18 +63,39 @@ def _paley2(q):
     return torch.cat([torch.cat([S + eye, S - eye], 1), torch.cat([S - eye, -S - eye], 1)], 0)
 
 
+# first halves (entries 0 .. (q - 1) / 2) of the symmetric first rows of the four circulants A, B, C, D, q = K / 4
+_WILLIAMSON = {
+    52: ("+-+--++", "+---+++", "++-+--+", "+----+-"),
+    156: ("+++--+-+-----+--++--", "++++---+--++----+-+-", "+++--++-+---+-+--+--", "+---++-+-+-----+++-+"),
+    172: ("+---++--++++-+-+++-++-", "++-++++++----+-+--++-+", "+++-+-++--+-+-++++-+--", "++---++++-+--+--++----"),
+}
+
+
+def _williamson(K):
+    q = K // 4
+    blocks = []
+    for half in _WILLIAMSON[K]:
+        h = [1.0 if c == "+" else -1.0 for c in half]
+        row = torch.tensor(h + h[1:][::-1][: q - len(h)])          # symmetric: r[i] == r[q - i]
+        assert row.numel() == q and torch.equal(row[1:], row[1:].flip(0))
+        blocks.append(torch.stack([torch.roll(row, i) for i in range(q)]))
+    A, B, C, D = blocks
+    return torch.cat([torch.cat([A, B, C, D], 1), torch.cat([-B, A, -D, C], 1),
+                      torch.cat([-C, D, A, -B], 1), torch.cat([-D, -C, B, A], 1)], 0)
+
+
 @functools.lru_cache(maxsize=None)
 def _had(K):
-    if K in (12, 20, 44, 60):
+    if K in (12, 20, 44, 60, 108, 140):
         return _paley1(K - 1)
+    if K in _WILLIAMSON:
+        return _williamson(K)
     if K in (28, 36):
         return _paley2(K // 2 - 1)
     if K == 40:
         h = _had(20)
         return torch.cat([torch.cat([h, h], 1), torch.cat([h, -h], 1)], 0)
-    raise NotImplementedError(
-        f"the {K} x {K} Hadamard block of the reference (hadamard_utils.py) is a tabulated Williamson-type matrix that "
-        "is not generated here")
+    raise NotImplementedError(f"no {K} x {K} Hadamard block in the reference (hadamard_utils.py:17-85)")
 
 
 def get_hadK(n, transpose=False):
@@ -96,15 +120,15 @@ def _dt(t):
 
 
 def _bits(hadK):
+    """host sign table of lcb_hadamard_rows: one 64-bit word per row for K <= 64, three per row above (include/lcb200.h)"""
     K = hadK.shape[0]
-    words = (ctypes.c_uint64 * K)()
+    wpr = 1 if K <= 64 else 3
+    words = (ctypes.c_uint64 * (K * wpr))()
     neg = (hadK < 0).tolist()
     for r in range(K):
-        w = 0
         for c in range(K):
             if neg[r][c]:
-                w |= 1 << c
-        words[r] = w
+                words[r * wpr + (c >> 6)] |= 1 << (c & 63)
     return words
 
 

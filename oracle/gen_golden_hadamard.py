@@ -31,11 +31,11 @@ GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 def main():
     out = {}
-    for K in (12, 20, 28, 36, 40, 44, 60):
+    for K in (12, 20, 28, 36, 40, 44, 60, 52, 108, 140, 156, 172):
         H = getattr(HU, "get_had%d" % K)().numpy()
         assert set(np.unique(H)) == {-1.0, 1.0}
         out["had%d" % K] = np.packbits(H < 0)
-    sizes = [16, 64, 96, 160, 224, 288, 352, 480, 2048, 2560, 3072]
+    sizes = [16, 64, 96, 160, 224, 288, 352, 480, 2048, 2560, 3072, 208, 216, 280, 312, 344, 11008]
     for n in sizes:
         g = torch.Generator().manual_seed(n)
         X = torch.randn(3, n, generator=g, dtype=torch.float64)
@@ -77,7 +77,7 @@ def main():
     RU.apply_exact_had_to_linear = HU_cuda
     for k, v in m.state_dict().items():
         out["rot_out/" + k] = GD.bits(v) if v.dtype == torch.bfloat16 else v.numpy()
-    out["__meta__"] = np.array(repr(dict(sizes=sizes, rand=[64, 96, 160], ks=[12, 20, 28, 36, 40, 44, 60], rot_seed=7)))
+    out["__meta__"] = np.array(repr(dict(sizes=sizes, rand=[64, 96, 160], ks=[12, 20, 28, 36, 40, 44, 60, 52, 108, 140, 156, 172], rot_seed=7)))
     np.savez_compressed(os.path.join(GOLD, "hadamard.npz"), **out)
     print("wrote hadamard.npz", os.path.getsize(os.path.join(GOLD, "hadamard.npz")))
 

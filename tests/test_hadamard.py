@@ -16,7 +16,7 @@ Z, META = gio.load("hadamard")
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("K", [12, 20, 28, 36, 40, 44, 60])
+@pytest.mark.parametrize("K", [12, 20, 28, 36, 40, 44, 60, 52, 108, 140, 156, 172])
 def test_generated_hadK_equals_reference_table(K):
     from llm_compressor_b200 import hadamard as H
     neg = np.unpackbits(Z["had%d" % K])[: K * K].reshape(K, K).astype(bool)
@@ -30,8 +30,8 @@ def test_get_hadK_precedence_and_unsupported():
     from llm_compressor_b200 import hadamard as H
     assert H.get_hadK(2560)[1] == 40 and H.get_hadK(3072)[1] == 12 and H.get_hadK(10240)[1] == 40
     assert H.get_hadK(8192) == (None, 1) and H.get_hadK(14336)[1] == 28
-    with pytest.raises(NotImplementedError):
-        H.get_hadK(11008)  # 172 * 64 (Llama-2-7B ffn): tabulated Williamson block, not generated
+    assert H.get_hadK(11008)[1] == 172 and H.get_hadK(13824)[1] == 108 and H.get_hadK(5120)[1] == 40   # Llama-2 7B / 13B ffn
+    assert H.get_hadK(6656)[1] == 52 and H.get_hadK(17920)[1] == 140 and H.get_hadK(19968)[1] == 156   # Llama-1 30B
     t = H.get_hadK(96, transpose=True)[0]
     assert torch.equal(t, H.get_hadK(96)[0].T)
 
@@ -70,7 +70,7 @@ def test_random_hadamard_matrix_same_seed_same_matrix(n):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("rows,n", [(512, 2048), (300, 2560), (256, 3072), (64, 8192), (32, 10240), (1000, 128), (77, 64),
-                                    (5, 12), (3, 16384)])
+                                    (5, 12), (3, 16384), (64, 11008), (16, 13824), (9, 6656)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_cuda_rotation_vs_oracle_and_dense_gemm(rows, n, dtype):
     """W @ R (R = diag(s) matmul_hadU(I)) at model widths: fast transform == oracle == the reference's dense fp64 GEMM."""
