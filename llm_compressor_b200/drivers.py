@@ -157,7 +157,9 @@ def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, da
     model.eval()
     sequential = model.get_sequential(mode="true")
     loader = _default_loader(model, n_samples, seq_len, dataloader)
+    n_total = None
     if dist_on:
+        n_total = sum(int(b[0].shape[0]) if hasattr(b[0], "shape") else 1 for b in loader)   # hooks count x.shape[0] per call
         loader = [loader[j] for j in parallel.sample_shard(len(loader))]     # this rank's calibration samples
     layers, inps, outs, layer_kwargs = _catch_inputs(model, device, loader)
     n_samples = inps.shape[0]
@@ -178,7 +180,7 @@ def gptq(model, device, n_samples=512, seq_len=2048, mse=False, verbose=True, da
             for j in range(n_samples):
                 layer(inps[j].unsqueeze(0), **layer_kwargs)
             handle.remove()
-            H = solvers.finalize_hessian(fq, all_reduce=dist_on)
+            H = solvers.finalize_hessian(fq, all_reduce=dist_on, n_total=n_total)
             by_group = {}
             for name in subset:
                 wq = subset[name].weight_quantizer

@@ -48,15 +48,20 @@ def row_shard(n_rows, rank=None, world_size=None):
     return slice(lo, min(n_rows, lo + per))
 
 
-def reduce_hessian_(H, nsamples, dxxt=None, group=None):
+def reduce_hessian_(H, nsamples, dxxt=None, group=None, n_total=None):
     """all-reduce(SUM) of the raw per-rank sums (and of the per-rank sample count).  Returns n_total; the
-    caller finalises ONCE with scale 2 / n_total (ops.hessian_finalize)."""
+    caller finalises ONCE with scale 2 / n_total (ops.hessian_finalize).
+    n_total: the number of samples over all ranks when the caller knows it (a static `sample_shard` split: the size of
+    the calibration set) -- skips the all-reduce of the counts and, with it, the host read-back that drains the stream
+    once per Hessian."""
     r, w = world()
     if w == 1:
         return nsamples
     dist.all_reduce(H, op=dist.ReduceOp.SUM, group=group)
     if dxxt is not None:
         dist.all_reduce(dxxt, op=dist.ReduceOp.SUM, group=group)
+    if n_total is not None:
+        return int(n_total)
     n = torch.tensor([float(nsamples)], dtype=torch.float64, device=H.device)
     dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
     return int(round(float(n.item())))

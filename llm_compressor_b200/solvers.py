@@ -47,17 +47,18 @@ def _accumulate(holder, x, dxxt=None, x_fp=None):
         holder._h_raw = True
 
 
-def finalize_hessian(holder, all_reduce=False):
+def finalize_hessian(holder, all_reduce=False, n_total=None):
     """Bring holder.H (and holder.dXXT) to the reference's running-mean value. Idempotent.
     all_reduce (sample-sharded calibration, one process per GPU): the raw per-rank sums and sample counts are summed over
-    the ranks first (parallel.reduce_hessian_), so every rank ends with the Hessian of ALL samples."""
+    the ranks first (parallel.reduce_hessian_), so every rank ends with the Hessian of ALL samples; n_total = the known size
+    of the whole calibration set lets that skip the count all-reduce and its host read-back."""
     if getattr(holder, "_h_raw", False):
         acc = getattr(holder, "_h_acc", None)
         if acc is not None:
             acc.flush()
             del holder._h_acc
         if all_reduce:
-            holder.nsamples = parallel.reduce_hessian_(holder.H, holder.nsamples, getattr(holder, "dXXT", None))
+            holder.nsamples = parallel.reduce_hessian_(holder.H, holder.nsamples, getattr(holder, "dXXT", None), n_total=n_total)
         scale = 2.0 / max(holder.nsamples, 1)
         ops.hessian_finalize(holder.H, scale, True)
         if getattr(holder, "dXXT", None) is not None:

@@ -61,7 +61,10 @@ def _hessian_case(rank, world):
     for j in mine:  # raw sums, as the lazy hook accumulates them
         S += X[j].astype(np.float64).T @ X[j].astype(np.float64)
     H = torch.from_numpy(S.astype(np.float32))
+    H2 = H.clone()
     n_tot = parallel.reduce_hessian_(H, len(mine))
+    # a statically split calibration set: the total is known, no count all-reduce / read-back; same sums
+    assert parallel.reduce_hessian_(H2, len(mine), n_total=n_samples) == n_tot and torch.equal(H, H2)
     H = H.numpy() * np.float32(2.0 / n_tot)
     Href = np.zeros((K, K), np.float32)
     n = 0
