@@ -719,6 +719,7 @@ struct TileArgs {
   int64_t ld;
   int k, nblk, c0, c1, with_inv, ntasks;
   int fi_nt;         // T-worker warps of factor_invert_split (1..6); 0 = the joint-worker factor_invert_la (A/B runs)
+  int gcols;         // columns per task group (1 = plain column-major order)
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -1302,14 +1303,37 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
       const int t = (int)atomicAdd(g.counter, 1u);
       int type = -1, ti = 0, tc = 0;
       if (t < g.ntasks) {
+        // Task order: columns in GROUPS of g.gcols; inside a group (columns cg .. ce - 1) first the small triangle of tiles on
+        // and right below the diagonal (the panel chain), then row by row the L tiles of ALL the group's columns, then the
+        // Y tiles the same way.  Tiles (i, c) and (i, c + 1) stream the same row i of the factor: handed out back to back
+        // they run at the same time on two SMs and the second finds the row in L2 (K = 8192: the factor no longer fits L2
+        // and every column sweep re-streamed it from HBM).  Every operand is still the result of a lower-numbered task.
         int rem = t;
-        for (int c = g.c0; c < g.c1; ++c) {
-          const int nl = nblk - c;
-          const int ny = g.with_inv ? (c - g.c0) : 0;
-          if (rem < nl) { type = 0; ti = c + rem; tc = c; break; }
-          rem -= nl;
-          if (rem < ny) { type = 1; ti = g.c0 + rem; tc = c; break; }
-          rem -= ny;
+        const int G = g.gcols;
+        for (int cg = g.c0; cg < g.c1; cg += G) {
+          const int ce = min(cg + G, g.c1), w = ce - cg;
+          const int n1 = (w * (w + 1)) >> 1;                 // (1) triangle, column-major
+          if (rem < n1) {
+            int j = 0;
+            while (rem >= w - j) { rem -= w - j; ++j; }
+            type = 0; tc = cg + j; ti = cg + j + rem; break;
+          }
+          rem -= n1;
+          const int n2 = (nblk - ce) * w;                    // (2) rows below the group, row-major
+          if (rem < n2) { type = 0; ti = ce + rem / w; tc = cg + rem % w; break; }
+          rem -= n2;
+          if (g.with_inv) {
+            const int n3 = (w * (w - 1)) >> 1;               // (3) Y tiles whose row lies inside the group, column-major
+            if (rem < n3) {
+              int j = 1;
+              while (rem >= j) { rem -= j; ++j; }
+              type = 1; tc = cg + j; ti = cg + rem; break;
+            }
+            rem -= n3;
+            const int n4 = (cg - g.c0) * w;                  // (4) Y tiles above the group, row-major
+            if (rem < n4) { type = 1; ti = g.c0 + rem / w; tc = cg + rem % w; break; }
+            rem -= n4;
+          }
         }
       }
       s_task[0] = type; s_task[1] = ti; s_task[2] = tc; s_task[3] = t;
@@ -1811,6 +1835,15 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
         fi = (e && e[0] >= '0' && e[0] <= '6') ? (e[0] - '0') : 4;
       }
       ta.fi_nt = fi;
+    }
+    {  // LCB_CHOL_GROUP=1..4: columns per task group.  Default 2 where a group's tasks still fit the grid at once (a larger
+       // group would stall the panel chain at every group boundary until enough of its tasks have retired)
+      static int gc = -1;
+      if (gc < 0) {
+        const char* e = getenv("LCB_CHOL_GROUP");
+        gc = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 0;
+      }
+      ta.gcols = gc > 0 ? gc : ((int)nblk * 2 <= sm_count() ? 2 : 1);
     }
     if (getenv("LCB_CHOL_TRACE")) {  // debug: task trace at byte offset lcb_chol_trace_offset(k) of the workspace
       ta.trace = reinterpret_cast<unsigned long long*>(w0 + tiles_trace_offset(k));
