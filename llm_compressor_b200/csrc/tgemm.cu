@@ -21,17 +21,23 @@ namespace lcb {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;  // BK fp32 = one 128 B swizzle row
+constexpr int BM = 128, BK = 32;            // BK fp32 = one 128 B swizzle row
 constexpr int UK = 8;                       // K per tf32 MMA
-constexpr int STAGES = 2;
 constexpr int A_BYTES = BM * BK * 4;        // 16384
-constexpr int B_BYTES = BN * BK * 4;        // 32768
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo planes: 98304
 constexpr int OUT_BUF_BYTES = 32 * 32 * 4;
 constexpr int OUT_BYTES = 4 * OUT_BUF_BYTES;  // one staging box per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 256 + 1024;
 constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 512;
+// Tile width BN = 256 (two TMEM accumulators of 256 columns, two 96 KB stages) for the big contractions; BN = 128 (three
+// 64 KB stages) for outputs of at most 128 columns -- the next-block update of the GPTQ chain, whose 256-wide tile
+// loaded and multiplied a half that was thrown away.
+template <int BN>
+struct Tile {
+  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo planes
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -56,6 +62,7 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
 }
 
 // c_format F32 (1) at [4,6), a/b format TF32 (2) at [7,10)/[10,13), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+template <int BN>
 constexpr uint32_t make_idesc_tf32() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -69,10 +76,13 @@ struct TgArgs {
   int nchunks;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ TgArgs a) {
+  constexpr int STAGES = Tile<BN>::STAGES, B_BYTES = Tile<BN>::B_BYTES, STAGE_BYTES = Tile<BN>::STAGE_BYTES;
+  constexpr int TMEM_COLS = Tile<BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* smem_out = smem + STAGES * STAGE_BYTES;
@@ -145,7 +155,7 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32();
+      constexpr uint32_t idesc = make_idesc_tf32<BN>();
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -308,6 +318,7 @@ int tgemm_nt(const float* Ah, const float* Al, int64_t lda, const float* Bh, con
   int rc;
   if ((rc = make_map_f32(&mah, Ah, M, Kd, lda, BK, BM)) != LCB_OK) return rc;
   if ((rc = make_map_f32(&mal, Al, M, Kd, lda, BK, BM)) != LCB_OK) return rc;
+  const int BN = N <= 128 ? 128 : 256;
   if ((rc = make_map_f32(&mbh, Bh, N, Kd, ldb, BK, BN)) != LCB_OK) return rc;
   if ((rc = make_map_f32(&mbl, Bl, N, Kd, ldb, BK, BN)) != LCB_OK) return rc;
   if ((rc = make_map_f32(&mc, C, M, N, ldc, 32, 32)) != LCB_OK) return rc;
@@ -315,10 +326,15 @@ int tgemm_nt(const float* Ah, const float* Al, int64_t lda, const float* Bh, con
   a.M = M; a.N = N; a.Kd = Kd; a.alpha = alpha; a.flags = flags;
   a.tiles_m = (int)ceil_div(M, BM); a.tiles_n = (int)ceil_div(N, BN);
   a.kcb = kcb; a.nchunks = nchunks;
-  LCB_CUDA(cudaFuncSetAttribute(tgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int tiles = a.tiles_m * a.tiles_n * nchunks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  tgemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, a);
+  if (BN == 128) {
+    LCB_CUDA(cudaFuncSetAttribute(tgemm_nt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<128>::SMEM_BYTES));
+    tgemm_nt_kernel<128><<<grid, NUM_THREADS, Tile<128>::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, a);
+  } else {
+    LCB_CUDA(cudaFuncSetAttribute(tgemm_nt_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<256>::SMEM_BYTES));
+    tgemm_nt_kernel<256><<<grid, NUM_THREADS, Tile<256>::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, a);
+  }
   LCB_LAUNCH_CHECK();
   return LCB_OK;
 }
