@@ -6,4 +6,3 @@ python bench.py --steps 1 --warmup 1 --layers 1 --no-cpu-baseline --no-fake-quan
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r2c_launches.csv python bench.py --steps 1 --warmup 1 --layers 1 --no-cpu-baseline --no-fake-quant > /dev/null 2>&1
 python scripts/summarize_launches.py $O/r2c_launches.csv > $O/r2c_launches_summary.txt; rm -f $O/r2c_launches.csv
 python scripts/chol_once.py 8192 && bash scripts/prof_one.sh r2c_chol_tiles_k8192 chol_tiles_tc 1 1 python scripts/chol_once.py 8192
-python scripts/update_once.py 5120 3072 1 && bash scripts/prof_one.sh r2c_tgemm_bn128 "tgemm_nt_kernel<128>" 6 1 python scripts/update_once.py 5120 3072 1
