@@ -720,6 +720,7 @@ struct TileArgs {
   int k, nblk, c0, c1, with_inv, ntasks;
   int fi_nt;         // T-worker warps of factor_invert_split (1..6); 0 = the joint-worker factor_invert_la (A/B runs)
   int gcols;         // columns per task group (1 = plain column-major order)
+  int use_tma;       // operand chunks by TMA (one producer thread) instead of cp.async from 224 threads
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -1265,13 +1266,17 @@ constexpr int TT_DRAIN = 8;                          // chunks per TMEM accumula
 static_assert(TT_STAGES * TT_STAGE_BYTES >= FI_SMEM_FLOATS * 4, "potf2 scratch must fit in the pipeline buffers");
 static_assert(TT_STAGES * TT_STAGE_BYTES >= FS_SMEM_FLOATS * 4, "split potf2 scratch must fit in the pipeline buffers");
 
-__global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
+__global__ void __launch_bounds__(256, 1)
+chol_tiles_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                     const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapYlo,
+                     const __grid_constant__ TileArgs g) {
   extern __shared__ uint8_t tsm_raw[];
   uint8_t* sm = smem_align1024(tsm_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TT_DATA_BYTES);
   uint64_t* mma_done = bars;          // [TT_STAGES]
   uint64_t* acc_done = bars + TT_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TT_STAGES + 1);
+  uint64_t* full = bars + TT_STAGES + 2;   // [TT_STAGES] TMA form: the four planes of a chunk have landed
   __shared__ int s_task[4];
   __shared__ int s_cnt[2];
   const int tid = threadIdx.x;
@@ -1281,7 +1286,7 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
   const int nblk = g.nblk;
 
   if (tid == 0) {
-    for (int i = 0; i < TT_STAGES; ++i) mbar_init(&mma_done[i], 1);
+    for (int i = 0; i < TT_STAGES; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&full[i], 1); }
     mbar_init(acc_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1295,6 +1300,7 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)C0;
   uint32_t par_done = 0;   // bit i: parity to wait for on mma_done[i]
+  uint32_t par_full = 0;   // bit i: parity to wait for on full[i] (MMA thread of the TMA form)
   uint32_t par_acc = 0;
 
   for (;;) {
@@ -1428,7 +1434,72 @@ __global__ void __launch_bounds__(256, 1) chol_tiles_tc_kernel(TileArgs g) {
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncthreads();   // all eight warps: nobody starts the next accumulation chain while TMEM is still being read
     };
-    if (total > 0) {
+    if (total > 0 && g.use_tma) {
+      // ---- TMA form (default): thread 0 is the producer -- one cp.async.bulk.tensor per plane of a chunk (the SWIZZLE_128B box
+      // IS the layout tt_load_plane builds), armed on the stage's `full` mbarrier -- thread 224 issues the MMAs, and the other
+      // 254 threads only meet them at the drains.  Same look-ahead rules as the cp.async form below (two chunks ahead, flags
+      // checked without blocking unless the pipeline is dry), without its 224-thread issue loops and named barriers per chunk.
+      const CUtensorMap* mPh = isL ? &mapA : &mapY;
+      const CUtensorMap* mPl = isL ? &mapAlo : &mapYlo;
+      auto issue_tma = [&](int gch) {
+        const int s = gch % TT_STAGES;
+        const int kofs = (j0 + (gch >> 2)) * NB + (gch & 3) * 32;
+        uint8_t* st = sm + s * TT_STAGE_BYTES;
+        if ((gch & 3) == 0) asm volatile("fence.proxy.async.global;" ::: "memory");   // tiles acquired through flags -> async proxy
+        mbar_expect_tx(&full[s], (uint32_t)((diag ? 2 : 4) * TT_PLANE));
+        tma_load_2d(mPh, &full[s], st, kofs, ti * NB);
+        tma_load_2d(mPl, &full[s], st + 2 * TT_PLANE, kofs, ti * NB);
+        if (!diag) {
+          tma_load_2d(&mapA, &full[s], st + TT_PLANE, kofs, c * NB);
+          tma_load_2d(&mapAlo, &full[s], st + 3 * TT_PLANE, kofs, c * NB);
+        }
+      };
+      int issued = 0, chain = 0;
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous task used this memory through the generic proxy
+        poll_block(0);
+        issue_tma(0);
+        issued = 1;
+        if (total > 1) { issue_tma(1); issued = 2; }
+      }
+      for (int it = 0; it < total; ++it) {
+        const int s = it % TT_STAGES;
+        const bool do_drain = it == total - 1 || chain + 1 == TT_DRAIN;
+        if (tid == 0) {
+          if (issued <= it) {                                 // pipeline dry: chunk `it` opens a step whose tiles were not ready
+            poll_block(it);
+            issue_tma(it);
+            issued = it + 1;
+          }
+          if (it >= 1) {                                      // the stage of chunk it+2 is the stage of chunk it-1
+            const int sp = (it - 1) % TT_STAGES;
+            mbar_wait(&mma_done[sp], (par_done >> sp) & 1u);
+            par_done ^= 1u << sp;
+          }
+          while (issued < total && issued <= it + 2) {
+            if (!flags_ready(issued)) break;
+            issue_tma(issued);
+            ++issued;
+          }
+        } else if (tid == 224) {
+          mbar_wait(&full[s], (par_full >> s) & 1u);
+          par_full ^= 1u << s;
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t ph = smem_u32(sm + s * TT_STAGE_BYTES), pl = ph + 2 * TT_PLANE;
+          const uint32_t qh = diag ? ph : ph + TT_PLANE, ql = diag ? pl : pl + TT_PLANE;
+          tt_mma_chunk(tmem_base, ph, pl, qh, ql, chain == 0);
+          umma_commit(&mma_done[s]);
+          if (do_drain) umma_commit(acc_done);
+        }
+        if (do_drain) { drain(); chain = 0; } else { ++chain; }
+      }
+      if (tid == 0) {  // MMAs of the last chunk: complete (acc_done waited), consume its stage barrier phase
+        const int sp = (total - 1) % TT_STAGES;
+        mbar_wait(&mma_done[sp], (par_done >> sp) & 1u);
+        par_done ^= 1u << sp;
+      }
+      __syncthreads();
+    } else if (total > 0) {
       if (warp < 7) {
         // ---- loaders.  A step's tiles may not be flagged yet: thread 0 checks WITHOUT blocking while chunks are still
         // in flight and blocks only when the pipeline has run dry.
@@ -1733,6 +1804,25 @@ SideStreams* side_streams() {
   return &cache[dev];
 }
 
+// [k, k] fp32 matrix, boxes of 32 columns x 128 rows, SWIZZLE_128B: one operand chunk of the tile tasks
+static int make_tile_map(CUtensorMap* map, const float* base, int64_t k) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc != LCB_OK) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)k};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)NB};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (tile tasks, k = %lld) failed with CUresult %d", (long long)k, (int)r);
+    return LCB_ERR_CUDA;
+  }
+  return LCB_OK;
+}
+
 constexpr int TILES_FULL_MAX = 16384;  // largest K factored by one chol_tiles_tc_kernel launch (above: the panel-launch chain)
 static int tiles_mode() {             // LCB_CHOL_TILES=0: panel-launch chain (A/B runs)
   static int m = -1;
@@ -1849,9 +1939,24 @@ extern "C" int lcb_chol_inv_upper(const float* H, float* U, int64_t k, const int
       ta.trace = reinterpret_cast<unsigned long long*>(w0 + tiles_trace_offset(k));
       LCB_CUDA(cudaMemsetAsync(ta.trace, 0, ((size_t)ta.ntasks * 16 + TILES_TRACE_EXTRA) * sizeof(float), st));
     }
+    {  // LCB_CHOL_TMA=0: cp.async operand staging (A/B runs)
+      static int tm = -1;
+      if (tm < 0) {
+        const char* e = getenv("LCB_CHOL_TMA");
+        tm = (e && e[0] == '0') ? 0 : 1;
+      }
+      ta.use_tma = tm;
+    }
+    CUtensorMap mA, mAlo, mY, mYlo;
+    {
+      int mrc;
+      if ((mrc = make_tile_map(&mA, ta.A, k)) != LCB_OK || (mrc = make_tile_map(&mAlo, ta.Alo, k)) != LCB_OK ||
+          (mrc = make_tile_map(&mY, ta.Y, k)) != LCB_OK || (mrc = make_tile_map(&mYlo, ta.Ylo, k)) != LCB_OK)
+        return mrc;
+    }
     const unsigned grid = (unsigned)std::min<int64_t>(ta.ntasks, sm_count());
     LCB_CUDA(cudaFuncSetAttribute(chol_tiles_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
-    chol_tiles_tc_kernel<<<grid, 256, TT_SMEM, st>>>(ta);
+    chol_tiles_tc_kernel<<<grid, 256, TT_SMEM, st>>>(mA, mAlo, mY, mYlo, ta);
     LCB_LAUNCH_CHECK();
     dim3 gr((unsigned)ceil_div(k, 32), (unsigned)ceil_div(k, 32));
     reverse_out_t_kernel<<<gr, dim3(32, 8), 0, st>>>(U, ta.Y, ta.Ylo, k);
