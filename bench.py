@@ -321,8 +321,8 @@ def run_ours(args):
                     acc.add(X[j])
                 # raw partial sums over NVLink (no-op on 1 GPU); the split of the calibration set is static, so the total
                 # count is known without an all-reduce + host read-back per Hessian
-                n = parallel.reduce_hessian_(H, acc.flush(), n_total=N_SAMPLES)
-                ops.hessian_finalize(H, 2.0 / n, True)
+                # (N > 1: as the packed upper blocks, half the bytes; the same call finalizes: scale 2/n + mirror)
+                n = parallel.reduce_finalize_hessian_(H, acc.flush(), n_total=N_SAMPLES)
                 e1.record()
                 evs.append((e0, e1, 2.0 * SEQ_LEN * K * K * len(my_samples), K))
                 e2 = torch.cuda.Event(enable_timing=True)

@@ -144,6 +144,15 @@ int lcb_hessian_accum(float* H, float* dxxt, const void* x, const void* x_fp, in
 int lcb_hessian_accum_multi(float* H, const void* const* xs, int count, int64_t tokens, int64_t k, float alpha,
                             int upper_only, void* stream);
 int lcb_hessian_finalize(float* H, int64_t k, float scale, int symmetric_from_upper, void* stream);
+/* Token-sharded ranks (new work, the reference is single-device): only the upper triangle of the raw sums is
+ * meaningful, so the all-reduce can carry HALF the bytes.  lcb_hessian_pack_upper copies the upper 32 x 32 blocks of S [k, k]
+ * (block row bi, block column bj >= bi, nb = ceil(k / 32); block (bi, bj) at float 1024 * (bi*nb - bi*(bi-1)/2 + bj - bi),
+ * row-major, zero beyond k) into `packed` (lcb_hessian_packed_floats(k) floats); after the all-reduce of `packed`,
+ * lcb_hessian_finalize_packed writes H[i][j] = H[j][i] = scale * packed(min(i,j), max(i,j)) -- bit for bit what
+ * lcb_hessian_finalize(symmetric_from_upper = 1) makes of the same sums. */
+size_t lcb_hessian_packed_floats(int64_t k);
+int lcb_hessian_pack_upper(const float* S, int64_t k, float* packed, void* stream);
+int lcb_hessian_finalize_packed(const float* packed, float* H, int64_t k, float scale, void* stream);
 /* ref: wanda/core.py:92-105, ria/core.py:94-107:  s = beta*s + alpha * sum_t X[t,:]^2 */
 int lcb_rownorm_accum(float* s, const void* x, int64_t tokens, int64_t k, float alpha, float beta, void* stream);
 

@@ -123,6 +123,9 @@ _OPTIONAL = [
     ("lcb_hessian_ws_bytes", [_i64, _i64], _sz),
     ("lcb_hessian_accum", [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _i32, _vp, _sz, _vp], _i32),
     ("lcb_hessian_finalize", [_vp, _i64, _f32, _i32, _vp], _i32),
+    ("lcb_hessian_packed_floats", [_i64], _sz),
+    ("lcb_hessian_pack_upper", [_vp, _i64, _vp, _vp], _i32),
+    ("lcb_hessian_finalize_packed", [_vp, _vp, _i64, _f32, _vp], _i32),
     ("lcb_hessian_accum_multi", [_vp, _vp, _i32, _i64, _i64, _f32, _i32, _vp], _i32),
     ("lcb_rownorm_accum", [_vp, _vp, _i64, _i64, _f32, _f32, _vp], _i32),
     ("lcb_chol_ws_bytes", [_i64], _sz),

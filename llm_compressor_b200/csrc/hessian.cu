@@ -519,6 +519,47 @@ __global__ void finalize_sym_kernel(float* __restrict__ H, int64_t k, float scal
   }
 }
 
+// ---- packed upper triangle (token-sharded ranks all-reduce HALF the bytes of the raw sums) ----
+// The upper 32 x 32 blocks of S (block row bi, block column bj >= bi; nb = ceil(k / 32) per side) are laid end to end,
+// row of blocks after row of blocks: block (bi, bj) starts at float 1024 * (bi * nb - bi * (bi - 1) / 2 + bj - bi) and is
+// stored row-major (32 floats = one 128-byte line per row; elements beyond k are zero).  One CTA per upper block.
+__device__ __forceinline__ int64_t packed_block_offset(int bi, int bj, int nb) {
+  return 1024 * ((int64_t)bi * nb - (int64_t)bi * (bi - 1) / 2 + (bj - bi));
+}
+
+__global__ void __launch_bounds__(256) pack_upper_kernel(const float* __restrict__ S, int64_t k, float* __restrict__ packed) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  float* dst = packed + packed_block_offset(bi, bj, (int)gridDim.x);
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = (int64_t)bi * 32 + r, j = (int64_t)bj * 32 + tx;
+    dst[r * 32 + tx] = (i < k && j < k) ? S[i * k + j] : 0.f;
+  }
+}
+
+// H[i][j] = H[j][i] = scale * packed(min(i,j), max(i,j)): finalize_sym_kernel reading the packed sums
+__global__ void __launch_bounds__(256) finalize_packed_kernel(const float* __restrict__ packed, float* __restrict__ H,
+                                                              int64_t k, float scale) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = packed + packed_block_offset(bi, bj, (int)gridDim.x);
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = (int64_t)bi * 32 + r, j = (int64_t)bj * 32 + tx;
+    const float v = scale * src[r * 32 + tx];
+    if (i < k && j < k && (bi != bj || tx >= r)) H[i * k + j] = v;
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t jj = (int64_t)bj * 32 + r, ii = (int64_t)bi * 32 + tx;
+    if (jj < k && ii < k && (bi != bj ? true : tx < r)) H[jj * k + ii] = tile[tx][r];
+  }
+}
+
 // s[k] = beta * s[k] + alpha * sum_t x[t][k]^2      (32 x 8 threads: 64 channels per CTA)
 __global__ void __launch_bounds__(256) rownorm_kernel(float* __restrict__ s, const __nv_bfloat16* __restrict__ x,
                                                       int64_t tokens, int64_t k, float alpha, float beta) {
@@ -744,6 +785,28 @@ extern "C" int lcb_hessian_finalize(float* H, int64_t k, float scale, int symmet
   if (!symmetric_from_upper) return scale_inplace(H, k * k, scale, st);
   dim3 grid((unsigned)ceil_div(k, 32), (unsigned)ceil_div(k, 32));
   finalize_sym_kernel<<<grid, 256, 0, st>>>(H, k, scale);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" size_t lcb_hessian_packed_floats(int64_t k) {
+  if (k <= 0) return 0;
+  const size_t nb = (size_t)ceil_div(k, 32);
+  return nb * (nb + 1) / 2 * 1024;
+}
+
+extern "C" int lcb_hessian_pack_upper(const float* S, int64_t k, float* packed, void* stream) {
+  LCB_REQUIRE(S != nullptr && packed != nullptr && k > 0 && k <= 16384 * 4, "lcb_hessian_pack_upper: bad arguments");
+  dim3 grid((unsigned)ceil_div(k, 32), (unsigned)ceil_div(k, 32));
+  pack_upper_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, k, packed);
+  LCB_LAUNCH_CHECK();
+  return LCB_OK;
+}
+
+extern "C" int lcb_hessian_finalize_packed(const float* packed, float* H, int64_t k, float scale, void* stream) {
+  LCB_REQUIRE(H != nullptr && packed != nullptr && k > 0 && k <= 16384 * 4, "lcb_hessian_finalize_packed: bad arguments");
+  dim3 grid((unsigned)ceil_div(k, 32), (unsigned)ceil_div(k, 32));
+  finalize_packed_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, H, k, scale);
   LCB_LAUNCH_CHECK();
   return LCB_OK;
 }

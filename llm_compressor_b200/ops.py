@@ -64,6 +64,30 @@ def hessian_finalize(H, scale, symmetric):
     return H
 
 
+def hessian_pack_upper(H):
+    """The upper 32 x 32 blocks of the raw sums H [k, k], end to end in one contiguous fp32 buffer (layout: lcb200.h) --
+    what token-sharded ranks all-reduce instead of the whole matrix (half the bytes)."""
+    _need_cuda(H)
+    assert H.dtype == torch.float32 and H.is_contiguous() and H.dim() == 2 and H.shape[0] == H.shape[1]
+    L = _lib.lib()
+    packed = torch.empty(L.lcb_hessian_packed_floats(H.shape[0]), dtype=torch.float32, device=H.device)
+    with torch.cuda.device(H.device):
+        rc = L.lcb_hessian_pack_upper(_ptr(H), H.shape[0], _ptr(packed), _stream(H.device))
+    _lib.check(rc, "lcb_hessian_pack_upper")
+    return packed
+
+
+def hessian_finalize_packed(packed, H, scale):
+    """H[i][j] = H[j][i] = scale * packed(min(i,j), max(i,j)): hessian_finalize(H, scale, True) reading packed sums."""
+    _need_cuda(H, packed)
+    L = _lib.lib()
+    assert packed.dtype == torch.float32 and packed.is_contiguous() and packed.numel() == L.lcb_hessian_packed_floats(H.shape[0])
+    with torch.cuda.device(H.device):
+        rc = L.lcb_hessian_finalize_packed(_ptr(packed), _ptr(H), H.shape[0], float(scale), _stream(H.device))
+    _lib.check(rc, "lcb_hessian_finalize_packed")
+    return H
+
+
 def hessian_accum_raw(H, x, nsamples, dxxt=None, x_fp=None):
     """Lazy form of the hook: raw sums H += X^T X (upper-triangle tiles only), dXXT += (X_fp-X)^T X.
     Equal to the reference's running mean after hessian_finalize(H, 2/n, True)."""

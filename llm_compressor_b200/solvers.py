@@ -50,19 +50,23 @@ def _accumulate(holder, x, dxxt=None, x_fp=None):
 def finalize_hessian(holder, all_reduce=False, n_total=None):
     """Bring holder.H (and holder.dXXT) to the reference's running-mean value. Idempotent.
     all_reduce (sample-sharded calibration, one process per GPU): the raw per-rank sums and sample counts are summed over
-    the ranks first (parallel.reduce_hessian_), so every rank ends with the Hessian of ALL samples; n_total = the known size
+    the ranks first (parallel.reduce_finalize_hessian_), so every rank ends with the Hessian of ALL samples; n_total = the known size
     of the whole calibration set lets that skip the count all-reduce and its host read-back."""
     if getattr(holder, "_h_raw", False):
         acc = getattr(holder, "_h_acc", None)
         if acc is not None:
             acc.flush()
             del holder._h_acc
+        dxxt = getattr(holder, "dXXT", None)
         if all_reduce:
-            holder.nsamples = parallel.reduce_hessian_(holder.H, holder.nsamples, getattr(holder, "dXXT", None), n_total=n_total)
-        scale = 2.0 / max(holder.nsamples, 1)
-        ops.hessian_finalize(holder.H, scale, True)
-        if getattr(holder, "dXXT", None) is not None:
-            ops.hessian_finalize(holder.dXXT, scale, False)
+            # the symmetric H travels as its packed upper blocks (half the bytes); dXXT is not symmetric: whole matrix
+            holder.nsamples = parallel.reduce_finalize_hessian_(holder.H, holder.nsamples, n_total=n_total)
+            if dxxt is not None:
+                parallel.reduce_hessian_(dxxt, holder.nsamples, n_total=holder.nsamples)
+        else:
+            ops.hessian_finalize(holder.H, 2.0 / max(holder.nsamples, 1), True)
+        if dxxt is not None:
+            ops.hessian_finalize(dxxt, 2.0 / max(holder.nsamples, 1), False)
         holder._h_raw = False
     return holder.H
 

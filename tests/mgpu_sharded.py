@@ -30,9 +30,13 @@ def main():
     n = 0
     for j in parallel.sample_shard(8):
         n = ops.hessian_accum_raw(H, X[j * 256:(j + 1) * 256].unsqueeze(0), n)
+    Hp = H.clone()
     n = parallel.reduce_hessian_(H, n)
     assert n == 8
     ops.hessian_finalize(H, 2.0 / n, True)
+    # the packed form (upper 32 x 32 blocks only, half the bytes over NVLink): same Hessian up to the order of the ranks' sums
+    assert parallel.reduce_finalize_hessian_(Hp, n // parallel.world()[1], n_total=8) == 8
+    assert torch.equal(Hp, Hp.t()) and float((Hp - H).norm() / H.norm()) < 1e-6
     Hf = torch.zeros(K, K, device=dev)
     m = 0
     for j in range(8):

@@ -74,6 +74,76 @@ def _hessian_case(rank, world):
     return dict(n_tot=n_tot, mine=mine, rel=rel, H=H)
 
 
+class _NumpyPacked:
+    """CPU stand-in for lcb_hessian_pack_upper / lcb_hessian_finalize_packed / lcb_hessian_finalize (csrc/hessian.cu; layout in
+    include/lcb200.h), so that parallel.reduce_finalize_hessian_ runs under gloo without a GPU.  TEST CODE ONLY; the same class
+    is the checker of the CUDA kernels in tests/test_solvers_gpu.py::test_hessian_packed_upper_matches_finalize."""
+
+    @staticmethod
+    def offsets(k):
+        nb = -(-k // 32)
+        return nb, {(bi, bj): 1024 * (bi * nb - bi * (bi - 1) // 2 + bj - bi) for bi in range(nb) for bj in range(bi, nb)}
+
+    def hessian_pack_upper(self, H):
+        k = H.shape[0]
+        nb, off = self.offsets(k)
+        Hp = np.zeros((nb * 32, nb * 32), np.float32)
+        Hp[:k, :k] = H.numpy()
+        out = np.zeros(nb * (nb + 1) // 2 * 1024, np.float32)
+        for (bi, bj), o in off.items():
+            out[o:o + 1024] = Hp[bi * 32:(bi + 1) * 32, bj * 32:(bj + 1) * 32].reshape(-1)
+        return torch.from_numpy(out)
+
+    def hessian_finalize_packed(self, packed, H, scale):
+        k = H.shape[0]
+        nb, off = self.offsets(k)
+        Hp = np.zeros((nb * 32, nb * 32), np.float32)
+        for (bi, bj), o in off.items():
+            Hp[bi * 32:(bi + 1) * 32, bj * 32:(bj + 1) * 32] = packed.numpy()[o:o + 1024].reshape(32, 32)
+        U = np.triu(Hp[:k, :k]) * np.float32(scale)
+        H.copy_(torch.from_numpy(U + np.triu(U, 1).T))
+        return H
+
+    def hessian_finalize(self, H, scale, symmetric):
+        U = np.triu(H.numpy()) * np.float32(scale)
+        H.copy_(torch.from_numpy(U + np.triu(U, 1).T))
+        return H
+
+
+def _packed_hessian_case(rank, world):
+    """sample-sharded raw sums of the UPPER tiles only (what the lazy hooks leave), all-reduced as packed upper blocks:
+    equal on every rank, equal to all-reduce of the whole matrix + finalize, and the reference's running mean."""
+    from llm_compressor_b200 import parallel
+    orc, X, W = _inputs()
+    X = X[:, :, :200]                      # K = 200: a ragged last 32-block (200 = 6 * 32 + 8)
+    n_samples, T, K = X.shape
+    mine = parallel.sample_shard(n_samples)
+    S = np.zeros((K, K), np.float64)
+    for j in mine:
+        S += X[j].astype(np.float64).T @ X[j].astype(np.float64)
+    S = S.astype(np.float32)
+    tile = np.add.outer(np.arange(K) // 32, -(np.arange(K) // 32)) <= 0     # 32-blocks touching the upper triangle
+    H = torch.from_numpy(np.where(tile, S, np.float32(-7.0)))               # garbage below: must not travel
+    full = torch.from_numpy(S.copy())
+    be = _NumpyPacked()
+    n_tot = parallel.reduce_finalize_hessian_(H, len(mine), backend=be)
+    H2 = torch.from_numpy(np.where(tile, S, np.float32(3.0)))
+    assert parallel.reduce_finalize_hessian_(H2, len(mine), n_total=n_samples, backend=be) == n_tot
+    parallel.reduce_hessian_(full, len(mine))
+    be.hessian_finalize(full, 2.0 / n_tot, True)
+    Href = np.zeros((K, K), np.float32)
+    n = 0
+    for j in range(n_samples):
+        n = orc.hessian_accum(Href, X[j], n)
+    rel = float(np.linalg.norm(H.numpy() - Href) / np.linalg.norm(Href))
+    nb = -(-K // 32)
+    # packed vs whole-matrix all-reduce: the same sums, but a ring adds the ranks in an order that depends on the element's
+    # offset in the buffer, so with 3 ranks the last bit may differ -- equal to ~1 ulp, not bit for bit
+    close = float((H - full).norm() / full.norm()) < 2e-7
+    return dict(n_tot=n_tot, rel=rel, same=bool(close and torch.equal(H, H2) and torch.equal(H, H.t())), H=H.numpy(),
+                packed_floats=int(be.hessian_pack_upper(full).numel()), expect_floats=nb * (nb + 1) // 2 * 1024)
+
+
 def _rows_case(rank, world):
     from llm_compressor_b200 import parallel
     orc, X, W = _inputs()
@@ -196,6 +266,14 @@ def test_sample_sharded_hessian_allreduce_matches_running_mean():
     assert sorted(res[0]["mine"] + res[1]["mine"]) == list(range(5))
     assert res[0]["rel"] < 1e-6 and res[1]["rel"] < 1e-6
     assert np.array_equal(res[0]["H"], res[1]["H"])
+
+
+def test_sample_sharded_hessian_packed_upper_allreduce():
+    for world in (2, 3):
+        res = _run("_packed_hessian_case", world)
+        assert all(r["n_tot"] == 5 and r["same"] and r["rel"] < 1e-6 for r in res), [(r["n_tot"], r["same"], r["rel"]) for r in res]
+        assert all(np.array_equal(res[0]["H"], r["H"]) for r in res)
+        assert res[0]["packed_floats"] == res[0]["expect_floats"] == 7 * 8 // 2 * 1024     # about half of 224 * 224
 
 
 def test_row_sharded_solve_allgather_is_bit_identical():

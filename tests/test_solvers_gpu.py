@@ -102,6 +102,32 @@ def test_hessian_shapes_vs_oracle(T, K):
     assert relf(to_f32_np(H), Href) < 1e-5 * max(1.0, T / 2048)
 
 
+@pytest.mark.parametrize("K", [200, 1000, 3072, 8192])
+def test_hessian_packed_upper_matches_finalize(K):
+    """The token-sharded ranks' packed all-reduce form (lcb_hessian_pack_upper -> lcb_hessian_finalize_packed):
+    bit for bit lcb_hessian_finalize(symmetric_from_upper) of the same raw sums, garbage below the diagonal tiles never
+    read, layout as written in include/lcb200.h (checked against the numpy stand-in of the gloo tests)."""
+    from test_parallel_cpu import _NumpyPacked
+    from llm_compressor_b200 import parallel
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(K)
+    X = torch.randn(512, K, generator=g).to(torch.bfloat16).to(DEV)
+    H = torch.tril(torch.full((K, K), 9.0, device=DEV), -1)   # junk everywhere below the diagonal: must never be read
+    ops.hessian_add(H, X, 1.0, 1.0, upper_only=True)
+    packed = ops.hessian_pack_upper(H)
+    nb = -(-K // 32)
+    assert packed.numel() == nb * (nb + 1) // 2 * 1024
+    if K <= 1000:
+        assert np.array_equal(packed.cpu().numpy(), _NumpyPacked().hessian_pack_upper(H.cpu()).numpy())
+    out = torch.full((K, K), 123.0, device=DEV)
+    ops.hessian_finalize_packed(packed, out, 0.25)
+    ref = ops.hessian_finalize(H.clone(), 0.25, True)
+    assert torch.equal(out, ref) and torch.equal(out, out.t())
+    # single process: parallel.reduce_finalize_hessian_ is the plain finalize
+    H1 = H.clone()
+    assert parallel.reduce_finalize_hessian_(H1, 8) == 8 and torch.equal(H1, ops.hessian_finalize(H.clone(), 2.0 / 8, True))
+
+
 def test_hessian_linearity_full_size():
     """K = 8192 (down_proj of Llama-3.2-3B), 2 samples: H(X1) + H(X2) == H([X1; X2]) scaled."""
     ops = _ops()
