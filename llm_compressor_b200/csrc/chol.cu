@@ -1789,6 +1789,11 @@ SideStreams* side_streams() {
     SideStreams& c = cache[dev];
     bool ok = true;
     for (int i = 0; i < 3; ++i) ok = ok && cudaStreamCreateWithFlags(&c.s[i], cudaStreamNonBlocking) == cudaSuccess;
+    int prio_least = 0, prio_greatest = 0;
+    ok = ok && cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&c.chain, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c.evIn, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c.evOut, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c.evP, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c.evT, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2; ++i) {

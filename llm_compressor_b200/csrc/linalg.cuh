@@ -68,6 +68,11 @@ int gemm_mode();
 struct SideStreams {
   cudaStream_t s[3];  // 0: B(q) panel updates, 1: S_B(J) strip updates, 2: triangular inverse of finished blocks
   cudaEvent_t evP, evB[2], evS[2], evT;
+  // the GPTQ block chain itself (quantiser + next-block update) runs on a stream of the GREATEST priority, fenced against the
+  // caller's stream by evIn / evOut: a chain GEMM that becomes ready while a look-ahead GEMM of a side stream (priority 0,
+  // the lowest there is -- the caller's stream cannot be put above them) still has CTAs to dispatch goes first
+  cudaStream_t chain;
+  cudaEvent_t evIn, evOut;
 };
 SideStreams* side_streams();
 

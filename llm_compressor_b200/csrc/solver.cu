@@ -7,6 +7,9 @@
 // a CTA owns 32 rows and never synchronises with other CTAs; 8 threads share a row (16 columns
 // each, held in registers), the 128x128 diagonal block of U (and P for GPTAQ) sits in shared
 // memory.  The trailing lazy-batch update W[:, i2:] -= Err @ U[i1:i2, i2:] is an fp32 GEMM.
+#include <atomic>
+#include <cstdlib>
+
 #include "linalg.cuh"
 #include "qmath.cuh"
 
@@ -268,6 +271,16 @@ using namespace lcb;
 static bool use_tg(const float* W, const float* U, const float* P, int64_t k) {
   return gemm_mode() == 1 && tg_ok(W, k) && tg_ok(U, k) && (P == nullptr || tg_ok(P, k));
 }
+static bool chain_prio_mode() {
+  static std::atomic<int> g{-1};
+  int m = g.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = std::getenv("LCB_CHAIN_PRIO");
+    m = e ? (std::atoi(e) != 0 ? 1 : 0) : 0;  // measured on B200: no gain (block loops 0.57-2.1 ms either way) -> off
+    g.store(m, std::memory_order_relaxed);
+  }
+  return m != 0;
+}
 static int64_t super_cols(int64_t k) { return std::min<int64_t>(SUPER, ceil_div(k, BLK) * BLK); }
 
 static size_t gptq_ws_floats(int64_t n, int64_t k, int block) {
@@ -338,9 +351,18 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
   if (P && (rc = split_tf32(P, k, (int)k, (int)k, PTh, PTl, k, 1, st)) != LCB_OK) return rc;
   SideStreams* ss = side_streams();
   if (ss == nullptr) return LCB_ERR_CUDA;
+  // The chain (quantiser + A(q) / S_A(J)) can move to the library's greatest-priority stream, between two events on the caller's
+  // stream when LCB_CHAIN_PRIO=1 (an A/B switch: measured, no gain, so the default stays on the caller's stream).
+  cudaStream_t const caller = st;
+  if (mode == MODE_QUANT && chain_prio_mode()) {  // SparseGPT's pre_block (select + the caller's all-reduce) stays on `caller`
+    LCB_CUDA(cudaEventRecord(ss->evIn, caller));
+    LCB_CUDA(cudaStreamWaitEvent(ss->chain, ss->evIn, 0));
+    st = ss->chain;
+  }
   auto fail = [&](int code) {
     cudaStreamSynchronize(ss->s[0]);
     cudaStreamSynchronize(ss->s[1]);
+    if (st != caller) cudaStreamSynchronize(st);
     return code;
   };
   // C[:, c0 : c0 + ncols] -= Err[:, e0 : e0 + kd] @ U[i1 + .., c0 ..]  (+ W1 @ P) on stream `s`
@@ -403,6 +425,10 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
   for (int e = 0; e < 2; ++e) {
     if (evB_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evB[e], 0));
     if (evS_live[e]) LCB_CUDA(cudaStreamWaitEvent(st, ss->evS[e], 0));
+  }
+  if (st != caller) {
+    LCB_CUDA(cudaEventRecord(ss->evOut, st));
+    LCB_CUDA(cudaStreamWaitEvent(caller, ss->evOut, 0));
   }
   return LCB_OK;
 }
