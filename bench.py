@@ -287,6 +287,7 @@ def run_ours(args):
             self.weight_quantizer = lc.FakeQuantizer.build(WCFG).to(dev)
 
     stage_evs = []  # (hessian end, factorize end, update end) events of the last step
+    stage_bufs, stage_free, results = {}, {}, []   # e2e: static H2D staging buffers, their "free again" events, live results
     want_sum, chk = [False], {"sum_abs": 0.0, "sum_sq": 0.0, "zeros": 0, "elements": 0}
 
     def one_model(from_host):
@@ -299,10 +300,20 @@ def run_ours(args):
         def prefetch(layer, gi):  # H2D of one group's weights on the copy stream (pinned -> HBM)
             if not from_host or layer >= args.layers:
                 return
+            wh = weights_host[layer][gi]
+            # rows are sharded over the ranks for the solve: each rank stages only its own rows -- into one of two
+            # STATIC device buffers per group (allocated once): a tensor allocated on the copy stream per prefetch and handed to
+            # the compute stream makes the caching allocator track cross-stream events, and blocks whose events are still
+            # pending are not reusable, so the timed steps kept falling back to cudaMalloc (a device synchronisation each)
+            src = wh[parallel.row_shard(wh.shape[0])]
+            key = (gi, layer & 1)
+            if key not in stage_bufs:
+                stage_bufs[key] = torch.empty(src.shape, dtype=src.dtype, device=dev)
+            w = stage_bufs[key]
             with torch.cuda.stream(copy_stream):
-                wh = weights_host[layer][gi]
-                # rows are sharded over the ranks for the solve: each rank stages only its own rows
-                w = wh[parallel.row_shard(wh.shape[0])].to(dev, non_blocking=True)
+                if key in stage_free:                      # the solve that last read this buffer (two layers ago) is done
+                    copy_stream.wait_event(stage_free[key])
+                w.copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             staged[(layer, gi)] = (w, ev)
@@ -332,9 +343,8 @@ def run_ours(args):
                 ntot = weights_dev[layer][gi].shape[0]
                 rows = parallel.row_shard(ntot)  # rows are independent given U: shard them over ranks
                 if from_host:
-                    w, ev = staged.pop((layer, gi))   # this rank's rows only
+                    w, ev = staged.pop((layer, gi))   # this rank's rows only (a static staging buffer)
                     cur.wait_event(ev)
-                    w.record_stream(cur)
                 else:
                     w = weights_dev[layer][gi][rows]
                 # the group's Linears as one stacked problem (solvers.update_weights_shared does this stacking
@@ -355,12 +365,14 @@ def run_ours(args):
                     done = torch.cuda.Event()
                     done.record(cur)
                     mine = lin.weight.data  # every rank writes its own rows of the result to the host buffer
+                    stage_free[(gi, layer & 1)] = done   # ... and the staging buffer may take the weights of layer + 2
                     with torch.cuda.stream(d2h_stream):
                         d2h_stream.wait_event(done)
                         out_host[layer][gi][rows].copy_(mine, non_blocking=True)
-                    mine.record_stream(d2h_stream)
+                    results.append(mine)   # kept alive until the D2H stream has been joined (no record_stream bookkeeping)
         if from_host:
             cur.wait_stream(d2h_stream)  # the step ends when the last result has reached the host buffer
+        results.clear()
         return evs
 
     def timed(from_host, steps):
