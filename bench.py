@@ -309,6 +309,11 @@ def run_ours(args):
             key = (gi, layer & 1)
             if key not in stage_bufs:
                 stage_bufs[key] = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                # the block comes from the compute stream's pool and may be a just-freed temporary that kernels already
+                # enqueued there still write: the copy stream must not touch it before they are done
+                first = torch.cuda.Event()
+                first.record(cur)
+                stage_free[key] = first
             w = stage_bufs[key]
             with torch.cuda.stream(copy_stream):
                 if key in stage_free:                      # the solve that last read this buffer (two layers ago) is done
