@@ -281,6 +281,16 @@ static bool chain_prio_mode() {
   }
   return m != 0;
 }
+static int b_streams_mode() {   // LCB_UPDATE_BSTREAMS=1: every B(q) on one side stream (A/B runs); default 2: alternating
+  static std::atomic<int> g{-1};
+  int m = g.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = std::getenv("LCB_UPDATE_BSTREAMS");
+    m = (e && std::atoi(e) == 1) ? 1 : 2;
+    g.store(m, std::memory_order_relaxed);
+  }
+  return m;
+}
 static int64_t super_cols(int64_t k) { return std::min<int64_t>(SUPER, ceil_div(k, BLK) * BLK); }
 
 static size_t gptq_ws_floats(int64_t n, int64_t k, int block) {
@@ -362,6 +372,7 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
   auto fail = [&](int code) {
     cudaStreamSynchronize(ss->s[0]);
     cudaStreamSynchronize(ss->s[1]);
+    cudaStreamSynchronize(ss->s[2]);
     if (st != caller) cudaStreamSynchronize(st);
     return code;
   };
@@ -399,11 +410,15 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
       if (i2 < s1) {  // rest of the super-block, Kd = 128 (short last block: its zero padded columns add 0)
         const int kd = (int)std::min<int64_t>(BLK, S - a.eoff);
         const int64_t nA = std::min<int64_t>(BLK, s1 - i2), nB = s1 - i2 - nA;
-        if (nB > 0) {  // B(q): beyond the next block, side stream 0
+        if (nB > 0) {  // B(q): beyond the next block, on a side stream
+          // B(q) and B(q + 1) do not depend on each other (reduce-adds into W commute; each only needs its own quantiser), but on
+          // ONE side stream they ran back to back, and a B launch (~25 us) is longer than a chain step (quantiser + A(q)): the
+          // loop was paced by the side stream.  Alternating two streams lets consecutive B launches overlap.
+          cudaStream_t sb = ss->s[(b_streams_mode() == 2 && (q & 1)) ? 2 : 0];
           LCB_CUDA(cudaEventRecord(ss->evP, st));
-          LCB_CUDA(cudaStreamWaitEvent(ss->s[0], ss->evP, 0));
-          if ((rc = update(EH, EL, WH, WL, a.eoff, i1, i2 + nA, nB, kd, ss->s[0])) != LCB_OK) return fail(rc);
-          LCB_CUDA(cudaEventRecord(ss->evB[q & 1], ss->s[0]));
+          LCB_CUDA(cudaStreamWaitEvent(sb, ss->evP, 0));
+          if ((rc = update(EH, EL, WH, WL, a.eoff, i1, i2 + nA, nB, kd, sb)) != LCB_OK) return fail(rc);
+          LCB_CUDA(cudaEventRecord(ss->evB[q & 1], sb));
           evB_live[q & 1] = true;
         }
         if ((rc = update(EH, EL, WH, WL, a.eoff, i1, i2, nA, kd, st)) != LCB_OK) return fail(rc);  // A(q)
