@@ -291,7 +291,18 @@ static int b_streams_mode() {   // LCB_UPDATE_BSTREAMS=1: every B(q) on one side
   }
   return m;
 }
-static int64_t super_cols(int64_t k) { return std::min<int64_t>(SUPER, ceil_div(k, BLK) * BLK); }
+static int64_t super_width() {   // LCB_UPDATE_SUPER = 256 / 512 / 1024 (A/B runs); default SUPER
+  static std::atomic<int> g{-1};
+  int m = g.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = std::getenv("LCB_UPDATE_SUPER");
+    const int v = e ? std::atoi(e) : SUPER;
+    m = (v == 256 || v == 512 || v == 1024) ? v : SUPER;
+    g.store(m, std::memory_order_relaxed);
+  }
+  return m;
+}
+static int64_t super_cols(int64_t k) { return std::min<int64_t>(super_width(), ceil_div(k, BLK) * BLK); }
 
 static size_t gptq_ws_floats(int64_t n, int64_t k, int block) {
   const size_t exact = (size_t)(2 * n * block);
