@@ -48,7 +48,10 @@ inline GemmArgs gemm_args(const float* A, int64_t lda, const float* B, int64_t l
 //   TG_A_LOWER    A[m][k] == 0 for k > m  (k-loop cut per row tile)
 //   TG_A_UPPER    A[m][k] == 0 for k < m
 // Requirements: all bases 16 B aligned, leading dimensions multiples of 4.
-enum { TG_STORE = 1, TG_LOWER_OUT = 2, TG_A_LOWER = 4, TG_A_UPPER = 8 };
+//   TG_PDL        launch with programmatic stream serialization: the kernel's prologue (barriers, TMEM allocation, tensor-map
+//                 prefetch) overlaps the tail of the preceding kernel of the stream; it executes griddepcontrol.wait before it
+//                 touches global memory
+enum { TG_STORE = 1, TG_LOWER_OUT = 2, TG_A_LOWER = 4, TG_A_UPPER = 8, TG_PDL = 16 };
 // kchain > 0: the reduction is cut into accumulation chains of at most kchain columns, each reduce-added
 // into C separately.  The tensor core's fp32 accumulator truncates, so the error of one chain grows
 // linearly with its length (3 * kchain / 8 MMAs); 0 = one chain per tile.

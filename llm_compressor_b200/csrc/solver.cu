@@ -190,6 +190,10 @@ __global__ void __launch_bounds__(256) block_step_kernel(BlockArgs a) {
 // nothing inside the block depends on the in-block propagation (ref: gptq/core.py:249-262 with
 // group_size == block_size), so the block step is elementwise: q = QDQ(w) * MASK, e = (w - q) / diag(U).
 __global__ void __launch_bounds__(256) block_quant_kernel(BlockArgs a) {
+  // programmatic dependent launch (LCB_UPDATE_PDL; no-ops otherwise): let the GEMM that follows start its prologue, then wait
+  // until the kernel before this one (the GEMM that updated this block's columns) has completed and flushed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of the [n, BLK] block
   const int64_t row = idx / (BLK / 4);
   const int c0 = (int)(idx % (BLK / 4)) * 4;
@@ -291,6 +295,16 @@ static int b_streams_mode() {   // LCB_UPDATE_BSTREAMS=1: every B(q) on one side
   }
   return m;
 }
+static bool pdl_mode() {   // LCB_UPDATE_PDL=1: chain kernels of the GPTQ block loop with programmatic dependent launch
+  static std::atomic<int> g{-1};
+  int m = g.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = std::getenv("LCB_UPDATE_PDL");
+    m = (e && std::atoi(e) != 0) ? 1 : 0;
+    g.store(m, std::memory_order_relaxed);
+  }
+  return m != 0;
+}
 static int64_t super_width() {   // LCB_UPDATE_SUPER = 256 / 512 / 1024 (A/B runs); default SUPER
   static std::atomic<int> g{-1};
   int m = g.load(std::memory_order_relaxed);
@@ -326,8 +340,17 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(a.Q)) & 15) == 0 && k % 4 == 0;
   auto step = [&]() -> int {
     if (mode == MODE_QUANT && !P && a.group >= a.count && a.group > 0 && aligned16) {
-      block_quant_kernel<<<(unsigned)ceil_div(n * (BLK / 4), 256), 256, 0, st>>>(a);
-      LCB_LAUNCH_CHECK();
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)ceil_div(n * (BLK / 4), 256), 1, 1);
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = (tg && pdl_mode()) ? 1 : 0;
+      count_launch();
+      LCB_CUDA(cudaLaunchKernelEx(&cfg, block_quant_kernel, a));
       return LCB_OK;
     }
     if (mode == MODE_SPARSE) block_step_kernel<MODE_SPARSE, false><<<grid, 256, smem, st>>>(a);
@@ -388,10 +411,11 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
     return code;
   };
   // C[:, c0 : c0 + ncols] -= Err[:, e0 : e0 + kd] @ U[i1 + .., c0 ..]  (+ W1 @ P) on stream `s`
+  const bool pdl = pdl_mode() && !P;
   auto update = [&](float* EH, float* EL, float* WH, float* WL, int64_t e0, int64_t urow, int64_t c0, int64_t ncols,
                     int kd, cudaStream_t s) -> int {
     int r = tgemm_nt(EH + e0, EL + e0, S, UTh + c0 * k + urow, UTl + c0 * k + urow, k, W + c0, k, (int)n, (int)ncols, kd,
-                     -1.0f, 0, s);
+                     -1.0f, (pdl && s == st) ? TG_PDL : 0, s);
     if (r != LCB_OK || !P) return r;
     return tgemm_nt(WH + e0, WL + e0, S, PTh + c0 * k + urow, PTl + c0 * k + urow, k, W + c0, k, (int)n, (int)ncols, kd,
                     1.0f, 0, s);
@@ -421,6 +445,9 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
       if (i2 < s1) {  // rest of the super-block, Kd = 128 (short last block: its zero padded columns add 0)
         const int kd = (int)std::min<int64_t>(BLK, S - a.eoff);
         const int64_t nA = std::min<int64_t>(BLK, s1 - i2), nB = s1 - i2 - nA;
+        // PDL form: A(q) goes first so that it directly follows the quantiser in the stream (an event record in between would
+        // break the programmatic edge); B(q) then also waits for A(q), which its two steps of slack absorb
+        if (pdl && (rc = update(EH, EL, WH, WL, a.eoff, i1, i2, nA, kd, st)) != LCB_OK) return fail(rc);
         if (nB > 0) {  // B(q): beyond the next block, on a side stream
           // B(q) and B(q + 1) do not depend on each other (reduce-adds into W commute; each only needs its own quantiser), but on
           // ONE side stream they ran back to back, and a B launch (~25 us) is longer than a chain step (quantiser + A(q)): the
@@ -432,12 +459,13 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
           LCB_CUDA(cudaEventRecord(ss->evB[q & 1], sb));
           evB_live[q & 1] = true;
         }
-        if ((rc = update(EH, EL, WH, WL, a.eoff, i1, i2, nA, kd, st)) != LCB_OK) return fail(rc);  // A(q)
+        if (!pdl && (rc = update(EH, EL, WH, WL, a.eoff, i1, i2, nA, kd, st)) != LCB_OK) return fail(rc);  // A(q)
       }
     }
     if (s1 < k) {  // everything beyond the super-block, Kd = S
       const int kd = (int)(s1 - s0);
       const int64_t nA = std::min<int64_t>(S, k - s1), nB = k - s1 - nA;
+      if (pdl && (rc = update(EH, EL, WH, WL, 0, s0, s1, nA, kd, st)) != LCB_OK) return fail(rc);  // S_A(J) first (see A(q))
       if (nB > 0) {  // S_B(J): beyond the next super-block, side stream 1
         LCB_CUDA(cudaEventRecord(ss->evP, st));
         LCB_CUDA(cudaStreamWaitEvent(ss->s[1], ss->evP, 0));
@@ -445,7 +473,7 @@ static int run_block_loop(BlockArgs a, int mode, float* W, const float* U, const
         LCB_CUDA(cudaEventRecord(ss->evS[J & 1], ss->s[1]));
         evS_live[J & 1] = true;
       }
-      if ((rc = update(EH, EL, WH, WL, 0, s0, s1, nA, kd, st)) != LCB_OK) return fail(rc);  // S_A(J)
+      if (!pdl && (rc = update(EH, EL, WH, WL, 0, s0, s1, nA, kd, st)) != LCB_OK) return fail(rc);  // S_A(J)
     }
   }
   for (int e = 0; e < 2; ++e) {

@@ -133,6 +133,10 @@ tgemm_nt_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (TG_PDL; no-ops otherwise): everything above ran under the tail of the preceding kernel;
+  // let the next kernel of the stream start its own prologue, then wait until the preceding grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -328,14 +332,25 @@ int tgemm_nt(const float* Ah, const float* Al, int64_t lda, const float* Bh, con
   a.kcb = kcb; a.nchunks = nchunks;
   const int tiles = a.tiles_m * a.tiles_n * nchunks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (flags & TG_PDL) ? 1 : 0;
+  count_launch();
   if (BN == 128) {
     LCB_CUDA(cudaFuncSetAttribute(tgemm_nt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<128>::SMEM_BYTES));
-    tgemm_nt_kernel<128><<<grid, NUM_THREADS, Tile<128>::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, a);
+    cfg.dynamicSmemBytes = Tile<128>::SMEM_BYTES;
+    LCB_CUDA(cudaLaunchKernelEx(&cfg, tgemm_nt_kernel<128>, mah, mal, mbh, mbl, mc, a));
   } else {
     LCB_CUDA(cudaFuncSetAttribute(tgemm_nt_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<256>::SMEM_BYTES));
-    tgemm_nt_kernel<256><<<grid, NUM_THREADS, Tile<256>::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, a);
+    cfg.dynamicSmemBytes = Tile<256>::SMEM_BYTES;
+    LCB_CUDA(cudaLaunchKernelEx(&cfg, tgemm_nt_kernel<256>, mah, mal, mbh, mbl, mc, a));
   }
-  LCB_LAUNCH_CHECK();
   return LCB_OK;
 }
 
