@@ -273,13 +273,17 @@ class Wrapper:
         _accumulate(self, x[0].detach())
 
 
-def prune_weight(layer, device, sparsity_ratio, block_size=128, percdamp=0.01, shard_rows=False):
+def prune_weight(layer, device, sparsity_ratio, block_size=128, percdamp=0.01, shard_rows=False, all_reduce=False,
+                 n_total=None):
     """ref: pruning/sparsegpt/core.py:160-228.  `shard_rows=True` under torch.distributed (one process per GPU):
-    every rank factors the (all-reduced) Hessian, solves its slice of the output rows with the exact global
-    per-block threshold (parallel.sparsegpt_update_sharded) and the rows are all-gathered."""
+    every rank factors the Hessian of ALL samples, solves its slice of the output rows with the exact global per-block
+    threshold (parallel.sparsegpt_update_sharded) and the rows are all-gathered.  `all_reduce=True` when the
+    ranks' hooks saw different calibration samples (parallel.sample_shard): the raw sums are all-reduced first
+    (finalize_hessian; n_total = the size of the whole calibration set, if known) -- leave it False when every rank ran the
+    whole calibration set or already finalised with all_reduce."""
     W = layer.module.weight.data.clone()
     W = W.float().contiguous()
-    H = finalize_hessian(layer)
+    H = finalize_hessian(layer, all_reduce=all_reduce, n_total=n_total)
     del layer.H
     dead = ops.dead_fix(H)
     W.masked_fill_(dead.unsqueeze(0), 0)
