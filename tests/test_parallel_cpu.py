@@ -144,6 +144,38 @@ def _packed_hessian_case(rank, world):
                 packed_floats=int(be.hessian_pack_upper(full).numel()), expect_floats=nb * (nb + 1) // 2 * 1024)
 
 
+def _finalize_case(rank, world):
+    """solvers.finalize_hessian(all_reduce=True) end to end on CPU: the numpy stand-ins are patched over the three ops it
+    reaches (pack / finalize_packed / finalize), H travels packed, GPTAQ's non-symmetric dXXT travels whole."""
+    from llm_compressor_b200 import ops, parallel, solvers
+    orc, X, W = _inputs()
+    X = X[:, :, :96]
+    n_samples, T, K = X.shape
+    be = _NumpyPacked()
+    ops.hessian_pack_upper, ops.hessian_finalize_packed = be.hessian_pack_upper, be.hessian_finalize_packed
+
+    def finalize(H, scale, symmetric):
+        return be.hessian_finalize(H, scale, True) if symmetric else H.mul_(scale)
+    ops.hessian_finalize = finalize
+    mine = parallel.sample_shard(n_samples)
+    S = np.zeros((K, K), np.float64)
+    D = np.zeros((K, K), np.float64)
+    for j in mine:
+        x = X[j].astype(np.float64)
+        S += x.T @ x
+        D += (0.5 * x[::-1]).T @ x          # any non-symmetric per-sample product
+    holder = type("Holder", (), {})()
+    holder.H, holder.dXXT = torch.from_numpy(np.triu(S).astype(np.float32)), torch.from_numpy(D.astype(np.float32))
+    holder.nsamples, holder._h_raw = len(mine), True
+    H = solvers.finalize_hessian(holder, all_reduce=True, n_total=n_samples)
+    Sall = sum(X[j].astype(np.float64).T @ X[j].astype(np.float64) for j in range(n_samples)) * (2.0 / n_samples)
+    Dall = sum((0.5 * X[j].astype(np.float64)[::-1]).T @ X[j].astype(np.float64) for j in range(n_samples)) * (2.0 / n_samples)
+    again = solvers.finalize_hessian(holder, all_reduce=True, n_total=n_samples)      # idempotent: no second all-reduce
+    return dict(n=holder.nsamples, relH=float(np.linalg.norm(H.numpy() - Sall) / np.linalg.norm(Sall)),
+                relD=float(np.linalg.norm(holder.dXXT.numpy() - Dall) / np.linalg.norm(Dall)),
+                sym=bool(torch.equal(H, H.t())), same=again is H)
+
+
 def _rows_case(rank, world):
     from llm_compressor_b200 import parallel
     orc, X, W = _inputs()
@@ -274,6 +306,11 @@ def test_sample_sharded_hessian_packed_upper_allreduce():
         assert all(r["n_tot"] == 5 and r["same"] and r["rel"] < 1e-6 for r in res), [(r["n_tot"], r["same"], r["rel"]) for r in res]
         assert all(np.array_equal(res[0]["H"], r["H"]) for r in res)
         assert res[0]["packed_floats"] == res[0]["expect_floats"] == 7 * 8 // 2 * 1024     # about half of 224 * 224
+
+
+def test_finalize_hessian_all_reduce_host_logic():
+    for r in _run("_finalize_case", 2):
+        assert r["n"] == 5 and r["relH"] < 1e-6 and r["relD"] < 1e-6 and r["sym"] and r["same"], r
 
 
 def test_row_sharded_solve_allgather_is_bit_identical():
