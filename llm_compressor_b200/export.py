@@ -14,12 +14,11 @@ e4m3 factor and the fp32 per-matrix factor separately would not reproduce the cl
 Decoding (`unpack_weight`) is plain torch arithmetic in the weight dtype, op for op the reference's `(q - z) * s` /
 `q * s + z`; it is the checker of the format, not a hot path.
 """
-import ctypes
 
 import torch
 
 from . import _lib
-from .quantizers import FPQuantizer, INTQuantizer, MXQuantizer, NVFPQuantizer, _ptr, _stream
+from .quantizers import INTQuantizer, MXQuantizer, NVFPQuantizer, _ptr, _stream
 
 _FP4_LUT = [0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0]
 

@@ -20,7 +20,6 @@ reference's tables by tests/test_hadamard.py.
 """
 import ctypes
 import functools
-import math
 
 import torch
 

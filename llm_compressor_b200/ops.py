@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .quantizers import DeferredStatus, _ptr, _status_word, _stream
+from .quantizers import DeferredStatus, _ptr, _stream
 
 
 def _need_cuda(*ts):
