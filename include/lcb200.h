@@ -72,7 +72,7 @@ typedef struct lcb_quant_cfg {
   int32_t zero_point;  /* asymmetric */
   int32_t scale_ebits; /* MX shared-exponent bits (ref: mx_quant.py:63), 8 */
   int32_t mse;         /* find_params with the clip search (ref: int_quant.py:115-162): 80 shrink steps, |.|^2.4 error;
-                          INT / FP / MX, axis -1, cols % group == 0; else LCB_ERR_UNSUPPORTED */
+                          INT / FP / MX / symmetric NVFP, axis -1, cols % group == 0; else LCB_ERR_UNSUPPORTED */
   int32_t reserved[3];
 } lcb_quant_cfg;
 
